@@ -1,0 +1,89 @@
+/* nextla_b200.h -- C ABI of the B200-native replacement for NextLA.jl's recursive TRSM/TRMM path.
+ *
+ * Every entry point replaces one piece of the reference's Julia interface (paths relative to the
+ * NextLA.jl repository).  All matrices are column-major (Julia layout), device pointers unless the name
+ * says `_host`, element type selected by `dtype`.  All calls are asynchronous on `stream` (the reference
+ * does not synchronise either, src/rectrxm.jl:75) and return an int status (0 = NLA_OK); nothing throws
+ * or aborts across the ABI.  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef NEXTLA_B200_H
+#define NEXTLA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nla_context *nla_handle_t;
+
+enum nla_dtype { NLA_F64 = 0, NLA_F32 = 1, NLA_F16 = 2 }; /* Float64 / Float32 / Float16 (src/rectrxm.jl:101: T<:AbstractFloat) */
+
+enum nla_status {
+  NLA_OK = 0,
+  NLA_ERR_INVALID_CHAR = 1,   /* side/uplo/trans/func not in the documented set (the reference silently coerces, src/rectrxm.jl:105-123) */
+  NLA_ERR_INVALID_DIM = 2,    /* negative n/m or leading dimension too small */
+  NLA_ERR_INVALID_DTYPE = 3,
+  NLA_ERR_NULL_POINTER = 4,
+  NLA_ERR_CUDA = 5,           /* a CUDA runtime/driver call failed; nla_last_cuda_error() has the code */
+  NLA_ERR_NO_DEVICE = 6,
+  NLA_ERR_UNSUPPORTED = 7,
+  NLA_ERR_INVALID_HANDLE = 8
+};
+
+/* Library lifetime.  One handle per (host thread, device); re-entrant across handles, no global mutable state. */
+int nla_create(nla_handle_t *handle, int device);
+int nla_destroy(nla_handle_t handle);
+const char *nla_status_string(int status);
+int nla_last_cuda_error(nla_handle_t handle);
+int nla_version(void);
+
+/* unified_rectrxm!(side, uplo, transpose, alpha, func, A, B)            -- src/rectrxm.jl:43-76 (+ unified_rec :101-198)
+ *   func 'S': B <- alpha * op(A)^-1 * B (side 'L')  or  alpha * B * op(A)^-1 (side 'R')
+ *   func 'M': B <- alpha * op(A) * B                or  alpha * B * op(A)
+ * A is n x n (only the `uplo` triangle is read, non-unit diagonal), B is n x m (side 'L') or m x n (side 'R'),
+ * m = number of independent right-hand-side vectors.  'C' == 'T' for the real element types supported. */
+int nla_rectrxm(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
+                double alpha, const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
+
+/* Same operation with HOST buffers (pinned or pageable): stages A once and streams B through the device in
+ * RHS slabs, overlapping copies with compute; synchronous (returns when B_host holds the result).
+ * This is the end-to-end path bench.py reports as `e2e`. */
+int nla_rectrxm_host(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
+                     double alpha, const void *A_host, int64_t lda, void *B_host, int64_t ldb);
+
+/* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
+ * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
+ * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */
+int nla_trsm_leaf(nla_handle_t handle, char side, char uplo, int dtype, int64_t n, int64_t m,
+                  const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
+int nla_trmm_leaf(nla_handle_t handle, char side, char uplo, int dtype, int64_t n, int64_t m,
+                  const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
+int64_t nla_leaf_max(int dtype);
+
+/* GEMM_ADD!(A,B,C): C += A*B and GEMM_SUB!(A,B,C): A -= B*C                            -- src/matmul.jl:69-81
+ * exposed as one update: C(MxN) <- C + sign * opA(A)(MxK) * opB(B)(KxN), sign = +1 or -1, opX = 'N' or 'T'
+ * (the reference passes transposition through Transpose wrappers, src/matmul.jl:30-32,40-42). */
+int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, int64_t M, int64_t N, int64_t K, int sign,
+                    const void *A, int64_t lda, const void *B, int64_t ldb, void *C, int64_t ldc, void *stream);
+
+/* Tunables (the reference hard-codes its thresholds, src/rectrxm.jl:52,63).  Keys:
+ *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
+ *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
+ *   "streams"     number of RHS slabs run on concurrent streams (default 1)                         */
+int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
+int64_t nla_get_option(nla_handle_t handle, const char *key);
+
+/* Host-only introspection of the schedule that replaces the recursive splitter (src/rectrxm.jl:101-198): writes up to
+ * max_ops records of 6 int64 {kind (0 = leaf, 1 = GEMM update), c0, cn, k0, kn, carries_alpha} in launch order, in the
+ * normalised coordinates of DESIGN.md (leaf: diagonal block [c0, c0+cn); update: V[c0:c0+cn] +-= Teff[c,k] V[k0:k0+kn]).
+ * Returns the number of ops (may exceed max_ops) or a negative nla_status.  Needs no GPU. */
+int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t *ops, int64_t max_ops);
+
+/* Counters for bench.py: kernels launched by this handle since the last reset. */
+int64_t nla_launch_count(nla_handle_t handle, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXTLA_B200_H */

@@ -1,0 +1,285 @@
+"""nextla.jl_b200 -- host-side mirror (Python/ctypes) of NextLA.jl's `unified_rectrxm!` interface on top of
+the C-ABI CUDA library `libnextla_b200.so` (include/nextla_b200.h).
+
+The reference is a Julia package; Julia is not installed in this image, so the drop-in Julia method lives in
+`julia/NextLAB200.jl` (unexecuted here) and this module drives the *same* C ABI for tests and benchmarks.
+Function names and argument order follow the reference:
+
+  unified_rectrxm(side, uplo, transpose, alpha, func, A, B)   <- unified_rectrxm!  src/rectrxm.jl:43
+  LeftLowerTRSM(A, B) ... RightUpperTRSM(A, B)                 <- src/trsm.jl:128-150
+  LeftLowerTRMM(A, B) ... RightUpperTRMM(A, B)                 <- src/trmm.jl:332-389
+  GEMM_ADD(A, B, C)  (C += A*B),  GEMM_SUB(A, B, C)  (A -= B*C) <- src/matmul.jl:69-81
+  trsm(side, uplo, transa, diag, A, B, alpha), trmm(...)       <- src/trsm.jl:186-205, src/trmm.jl:430-448
+
+Matrices are column-major device arrays: 2-D torch CUDA tensors with stride (1, ld) (use `colmajor()` /
+`to_numpy()`).  Everything runs on the GPU through the library; there is NO CPU fallback -- importing is fine
+without a GPU, but any compute call raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnextla_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "nextla_b200.h")
+
+NLA_F64, NLA_F32, NLA_F16 = 0, 1, 2
+_lib = None
+_handles = {}
+
+
+class NextLAError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the CUDA library and declare the prototypes of every symbol in include/nextla_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NextLAError(f"{LIB_PATH} is missing: build it with `python nextla.jl_b200/build.py` (no CPU fallback exists)")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    H, I, L, D, P, CH = c.c_void_p, c.c_int, c.c_int64, c.c_double, c.c_void_p, c.c_char
+    protos = {
+        "nla_create": (I, [c.POINTER(H), I]),
+        "nla_destroy": (I, [H]),
+        "nla_status_string": (c.c_char_p, [I]),
+        "nla_last_cuda_error": (I, [H]),
+        "nla_version": (I, []),
+        "nla_rectrxm": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
+        "nla_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L]),
+        "nla_trsm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
+        "nla_trmm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
+        "nla_leaf_max": (L, [I]),
+        "nla_gemm_update": (I, [H, I, CH, CH, L, L, L, I, P, L, P, L, P, L, P]),
+        "nla_set_option": (I, [H, c.c_char_p, L]),
+        "nla_get_option": (L, [H, c.c_char_p]),
+        "nla_launch_count": (L, [H, I]),
+        "nla_plan": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
+            "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan"]
+
+
+def _check(rc: int, h=None):
+    if rc != 0:
+        lib = load_library()
+        msg = lib.nla_status_string(rc).decode()
+        if rc == 5 and h is not None:
+            msg += f" [cudaError {lib.nla_last_cuda_error(h)}]"
+        raise NextLAError(f"nextla_b200 status {rc}: {msg}")
+
+
+class Handle:
+    """Owns one nla_handle_t (one per device)."""
+
+    def __init__(self, device: int = 0):
+        lib = load_library()
+        self._h = ctypes.c_void_p()
+        _check(lib.nla_create(ctypes.byref(self._h), device))
+        self.device = device
+
+    def set_option(self, key: str, value: int):
+        _check(load_library().nla_set_option(self._h, key.encode(), int(value)), self._h)
+
+    def get_option(self, key: str) -> int:
+        return int(load_library().nla_get_option(self._h, key.encode()))
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(load_library().nla_launch_count(self._h, 1 if reset else 0))
+
+    def close(self):
+        if self._h:
+            load_library().nla_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_handle(device: Optional[int] = None) -> Handle:
+    import torch
+
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _handles:
+        _handles[device] = Handle(device)
+    return _handles[device]
+
+
+# ---- column-major device matrices ---------------------------------------------------------------
+_NP2DT = {np.dtype(np.float64): NLA_F64, np.dtype(np.float32): NLA_F32, np.dtype(np.float16): NLA_F16}
+
+
+def colmajor(a: np.ndarray, device: str = "cuda"):
+    """Host ndarray -> column-major torch CUDA tensor of the same logical shape (stride (1, rows))."""
+    import torch
+
+    a = np.asarray(a)
+    t = torch.from_numpy(np.ascontiguousarray(a.T)).to(device)
+    return t.t()
+
+
+def empty_colmajor(rows: int, cols: int, dtype, device: str = "cuda", ld: Optional[int] = None):
+    import torch
+
+    ld = rows if ld is None else ld
+    return torch.empty((cols, ld), dtype=dtype, device=device).t()[:rows, :]
+
+
+def to_numpy(t) -> np.ndarray:
+    return np.asfortranarray(t.detach().cpu().numpy())
+
+
+def _desc(t):
+    """(ptr, rows, cols, ld, dtype code) of a column-major 2-D torch CUDA tensor."""
+    import torch
+
+    if not t.is_cuda:
+        raise NextLAError("matrices must be CUDA tensors (no CPU fallback)")
+    if t.dim() != 2:
+        raise NextLAError("matrices must be 2-D")
+    rows, cols = t.shape
+    if rows > 1 and t.stride(0) != 1:
+        raise NextLAError("matrices must be column-major (stride(0) == 1); use nextla colmajor()")
+    ld = t.stride(1) if (cols > 1 and rows > 0) else max(1, rows)
+    if ld < max(1, rows):
+        raise NextLAError("invalid leading dimension")
+    code = {torch.float64: NLA_F64, torch.float32: NLA_F32, torch.float16: NLA_F16}.get(t.dtype)
+    if code is None:
+        raise NextLAError(f"unsupported dtype {t.dtype}")
+    return t.data_ptr(), rows, cols, ld, code
+
+
+def _stream_ptr(stream):
+    import torch
+
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ch(c: str) -> bytes:
+    if not isinstance(c, str) or len(c) != 1:
+        raise NextLAError(f"expected a single character, got {c!r}")
+    return c.encode()
+
+
+def unified_rectrxm(side: str, uplo: str, transpose: str, alpha: float, func: str, A, B, stream=None, handle: Optional[Handle] = None):
+    """unified_rectrxm!(side, uplo, transpose, alpha, func, A, B) -- src/rectrxm.jl:43-76.  In place on B; returns B.
+    Asynchronous on the current torch stream, like the reference (which does not synchronise, :75)."""
+    h = handle or default_handle(A.device.index)
+    pa, ar, ac, lda, dta = _desc(A)
+    pb, br, bc, ldb, dtb = _desc(B)
+    if dta != dtb:
+        raise NextLAError("A and B must have the same element type (src/rectrxm.jl:101)")
+    if ar != ac:
+        raise NextLAError("A must be square")
+    n = ar
+    m = bc if side == "L" else br
+    if (side == "L" and br != n) or (side == "R" and bc != n):
+        raise NextLAError("dimension mismatch between A and B")
+    rc = load_library().nla_rectrxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
+                                    _stream_ptr(stream))
+    _check(rc, h._h)
+    return B
+
+
+def unified_rectrxm_host(side, uplo, transpose, alpha, func, A: np.ndarray, B: np.ndarray, handle: Optional[Handle] = None, device: int = 0):
+    """Same operation on HOST column-major ndarrays (Fortran order); B is overwritten.  Synchronous."""
+    h = handle or default_handle(device)
+    if not (A.flags.f_contiguous and B.flags.f_contiguous) or A.dtype != B.dtype:
+        raise NextLAError("host matrices must be Fortran-ordered ndarrays of the same dtype")
+    n = A.shape[0]
+    m = B.shape[1] if side == "L" else B.shape[0]
+    rc = load_library().nla_rectrxm_host(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), _NP2DT[A.dtype], n, m, float(alpha),
+                                         A.ctypes.data, max(1, A.shape[0]), B.ctypes.data, max(1, B.shape[0]))
+    _check(rc, h._h)
+    return B
+
+
+def _leaf(solve: bool, side: str, uplo: str, A, B, stream=None, handle=None):
+    h = handle or default_handle(A.device.index)
+    pa, ar, ac, lda, dta = _desc(A)
+    pb, br, bc, ldb, dtb = _desc(B)
+    if dta != dtb or ar != ac:
+        raise NextLAError("bad leaf arguments")
+    n = ar
+    m = bc if side == "L" else br
+    fn = load_library().nla_trsm_leaf if solve else load_library().nla_trmm_leaf
+    _check(fn(h._h, _ch(side), _ch(uplo), dta, n, m, pa, lda, pb, ldb, _stream_ptr(stream)), h._h)
+    return B
+
+
+def LeftLowerTRSM(A, B, **kw): return _leaf(True, "L", "L", A, B, **kw)      # src/trsm.jl:128
+def LeftUpperTRSM(A, B, **kw): return _leaf(True, "L", "U", A, B, **kw)      # src/trsm.jl:134
+def RightLowerTRSM(A, B, **kw): return _leaf(True, "R", "L", A, B, **kw)     # src/trsm.jl:140
+def RightUpperTRSM(A, B, **kw): return _leaf(True, "R", "U", A, B, **kw)     # src/trsm.jl:146
+def LeftLowerTRMM(A, B, **kw): return _leaf(False, "L", "L", A, B, **kw)     # src/trmm.jl:332
+def LeftUpperTRMM(A, B, **kw): return _leaf(False, "L", "U", A, B, **kw)     # src/trmm.jl:352
+def RightLowerTRMM(A, B, **kw): return _leaf(False, "R", "L", A, B, **kw)    # src/trmm.jl:367
+def RightUpperTRMM(A, B, **kw): return _leaf(False, "R", "U", A, B, **kw)    # src/trmm.jl:384
+
+
+def _gemm(C, A, B, sign: int, transa="N", transb="N", stream=None, handle=None):
+    h = handle or default_handle(C.device.index)
+    pa, ar, ac, lda, dta = _desc(A)
+    pb, br, bc, ldb, dtb = _desc(B)
+    pc, M, N, ldc, dtc = _desc(C)
+    K = ac if transa == "N" else ar
+    if not (dta == dtb == dtc):
+        raise NextLAError("GEMM operands must share one element type")
+    _check(load_library().nla_gemm_update(h._h, dtc, _ch(transa), _ch(transb), M, N, K, sign, pa, lda, pb, ldb, pc, ldc, _stream_ptr(stream)), h._h)
+    return C
+
+
+def GEMM_ADD(A, B, C, **kw):
+    """GEMM_ADD!(A, B, C): C += A*B -- src/matmul.jl:69-74."""
+    return _gemm(C, A, B, +1, **kw)
+
+
+def GEMM_SUB(A, B, C, **kw):
+    """GEMM_SUB!(A, B, C): A -= B*C -- src/matmul.jl:76-81."""
+    return _gemm(A, B, C, -1, **kw)
+
+
+def trsm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
+    """trsm(side, uplo, transa, diag, A, B, alpha) -- src/trsm.jl:186-205.  Unlike the reference (which ignores
+    `transa` and is limited to one leaf) this honours `transa` and recurses; `diag` must be 'N'."""
+    if diag != "N":
+        raise NextLAError("unit-diagonal solves are not implemented (the reference ignores diag, src/trsm.jl:186)")
+    return unified_rectrxm(side, uplo, transa, alpha, "S", A, B, **kw)
+
+
+def trmm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
+    """trmm(side, uplo, transa, diag, A, B, alpha) -- src/trmm.jl:430-448."""
+    if diag != "N":
+        raise NextLAError("unit-diagonal products are not implemented (the reference ignores diag, src/trmm.jl:430)")
+    return unified_rectrxm(side, uplo, transa, alpha, "M", A, B, **kw)
+
+
+def plan(side: str, uplo: str, transpose: str, func: str, n: int, leaf: int = 0):
+    """Host-only: the launch schedule as a list of (kind, c0, cn, k0, kn, carries_alpha) tuples (kind 0 = leaf, 1 = update)."""
+    lib = load_library()
+    cnt = lib.nla_plan(_ch(side), _ch(uplo), _ch(transpose), _ch(func), n, leaf, None, 0)
+    if cnt < 0:
+        _check(-cnt)
+    buf = (ctypes.c_int64 * (6 * max(cnt, 1)))()
+    lib.nla_plan(_ch(side), _ch(uplo), _ch(transpose), _ch(func), n, leaf, buf, cnt)
+    return [tuple(buf[6 * i + j] for j in range(6)) for i in range(cnt)]

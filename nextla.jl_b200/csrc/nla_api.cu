@@ -1,0 +1,569 @@
+// nla_api.cu -- C ABI (include/nextla_b200.h), argument validation, the host-side schedule that replaces
+// the reference's recursive splitter (src/rectrxm.jl:43-198), and the kernel launchers.
+#include "../../include/nextla_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "gemm_f64.cuh"
+#include "gemm_simt.cuh"
+#include "leaf.cuh"
+
+using namespace nla;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct nla_context {
+  uint32_t magic;
+  int device;
+  int last_cuda;
+  int64_t launches;
+  EncodeTiledFn encode;
+  // options
+  int64_t leaf;         // recursion cutoff (0 = default)
+  int64_t force_simt;
+  int64_t nstreams;
+  // helper streams / events for concurrent RHS slabs
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t fork_event;
+  // device staging for the host-buffer entry point
+  void* stage_a; size_t stage_a_bytes;
+  void* stage_b; size_t stage_b_bytes;
+  cudaStream_t host_streams[3];
+  cudaEvent_t host_events[8];
+};
+
+static const uint32_t NLA_MAGIC = 0x4e4c4142u;  // "NLAB"
+
+#define NLA_CUDA(ctx, call)                                    \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) {                                  \
+      (ctx)->last_cuda = (int)e__;                             \
+      return NLA_ERR_CUDA;                                     \
+    }                                                          \
+  } while (0)
+
+static inline size_t dtype_size(int dtype) { return dtype == NLA_F64 ? 8 : dtype == NLA_F32 ? 4 : 2; }
+
+// --------------------------------------------------------------------------------------------------
+// The normalised problem.  Every (side, uplo, trans) combination is reduced to
+//        Y = Teff^-1 * V   (func 'S')      or      Y = Teff * V   (func 'M')
+// where the m right-hand-side vectors are the columns of B (side 'L') or the rows of B (side 'R'),
+// Teff = op(A) for side 'L' and op(A)^T for side 'R'.  This is the reference's own trick for `trans`
+// (lazy Transpose + flipped uplo, src/rectrxm.jl:56-59) extended to the side.
+// --------------------------------------------------------------------------------------------------
+struct Problem {
+  int dtype;
+  bool solve, right;
+  bool teff_trans;   // Teff(r,k) = A[k,r] instead of A[r,k]
+  bool lower;        // Teff lower triangular
+  int64_t n, m;
+  double alpha;
+  const void* A; int64_t lda;
+  void* B; int64_t ldb;
+  int64_t es, vs;    // element / vector strides inside B
+};
+
+struct Op {
+  enum Kind { LEAF, GEMM } kind;
+  int64_t off, sz;          // LEAF: diagonal block [off, off+sz)
+  int64_t c0, cn, k0, kn;   // GEMM: V[c0:c0+cn] += sgn * Teff[c-range, k-range] * V[k0:k0+kn]
+  double pre, post;         // LEAF scalings; GEMM uses pre as beta
+};
+
+// Flatten the reference's recursion (src/rectrxm.jl:101-198) into an ordered op list.
+// Split rule identical to the reference (:129-134).  `scaled`: for 'S' the block already carries alpha
+// (the reference scales all of B up front, :64; here alpha is folded into the first kernel that touches a
+// block).  `final`: for 'M' no later update touches the block, so alpha (:72) is folded into this one.
+static void build_schedule(const Problem& P, int64_t leaf, int64_t off, int64_t n, bool scaled, bool final, std::vector<Op>& ops) {
+  if (n <= leaf) {
+    Op o{};
+    o.kind = Op::LEAF; o.off = off; o.sz = n;
+    o.pre = (P.solve && !scaled) ? P.alpha : 1.0;
+    o.post = (!P.solve && final) ? P.alpha : 1.0;
+    ops.push_back(o);
+    return;
+  }
+  int64_t mid;
+  if ((n & (n - 1)) == 0) mid = n / 2; else { mid = 1; while (mid * 2 < n) mid *= 2; }
+  const int64_t rem = n - mid;
+  Op g{};
+  g.kind = Op::GEMM;
+  if (P.solve) {
+    if (P.lower) {  // forward: first block, update second, second block      (:159-176)
+      build_schedule(P, leaf, off, mid, scaled, false, ops);
+      g.c0 = off + mid; g.cn = rem; g.k0 = off; g.kn = mid; g.pre = scaled ? 1.0 : P.alpha; g.post = 1.0;
+      ops.push_back(g);
+      build_schedule(P, leaf, off + mid, rem, true, false, ops);
+    } else {        // backward: second block, update first, first block       (:178-197)
+      build_schedule(P, leaf, off + mid, rem, scaled, false, ops);
+      g.c0 = off; g.cn = mid; g.k0 = off + mid; g.kn = rem; g.pre = scaled ? 1.0 : P.alpha; g.post = 1.0;
+      ops.push_back(g);
+      build_schedule(P, leaf, off, mid, true, false, ops);
+    }
+  } else {
+    if (P.lower) {  // second block rows need the ORIGINAL first block: multiply second, add, multiply first
+      build_schedule(P, leaf, off + mid, rem, false, false, ops);
+      g.c0 = off + mid; g.cn = rem; g.k0 = off; g.kn = mid; g.pre = 1.0; g.post = final ? P.alpha : 1.0;
+      ops.push_back(g);
+      build_schedule(P, leaf, off, mid, false, final, ops);
+    } else {
+      build_schedule(P, leaf, off, mid, false, false, ops);
+      g.c0 = off; g.cn = mid; g.k0 = off + mid; g.kn = rem; g.pre = 1.0; g.post = final ? P.alpha : 1.0;
+      ops.push_back(g);
+      build_schedule(P, leaf, off + mid, rem, false, final, ops);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// launchers
+// --------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_leaf(nla_context* ctx, const Problem& P, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+  LeafParams<T> lp;
+  const T* A = (const T*)P.A + o.off * (P.lda + 1);
+  lp.A = A;
+  lp.a_rs = P.teff_trans ? P.lda : 1;
+  lp.a_cs = P.teff_trans ? 1 : P.lda;
+  lp.lower = P.lower; lp.t = (int)o.sz;
+  lp.V = (T*)P.B + o.off * P.es + v0 * P.vs;
+  lp.es = P.es; lp.vs = P.vs; lp.m = nv;
+  lp.pre = o.pre; lp.post = o.post;
+  const size_t smem = leaf_smem_bytes<T>((int)o.sz);
+  const unsigned grid = (unsigned)((nv + LEAF_W - 1) / LEAF_W);
+  if (P.solve) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(leaf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    leaf_kernel<T, true><<<grid, LEAF_W, smem, st>>>(lp);
+  } else {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(leaf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    leaf_kernel<T, false><<<grid, LEAF_W, smem, st>>>(lp);
+  }
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+// generic strided GEMM: C(MxN) <- post*(beta*C + sgn*A*B)
+template <typename T>
+static int launch_gemm_simt(nla_context* ctx, int64_t M, int64_t N, int64_t K, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
+                            int64_t b_rs, int64_t b_cs, T* C, int64_t ldc, double beta, double sgn, double post, cudaStream_t st) {
+  GemmSimtParams<T> gp;
+  gp.M = (int)M; gp.N = (int)N; gp.K = (int)K;
+  gp.A = A; gp.a_rs = a_rs; gp.a_cs = a_cs;
+  gp.B = B; gp.b_rs = b_rs; gp.b_cs = b_cs;
+  gp.C = C; gp.ldc = ldc; gp.beta = beta; gp.sgn = sgn; gp.post = post;
+  dim3 grid((unsigned)((M + GS_BM - 1) / GS_BM), (unsigned)((N + GS_BN - 1) / GS_BN));
+  gemm_simt_kernel<T><<<grid, GS_THREADS, 0, st>>>(gp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+// TMA descriptor for a column-major FP64 matrix (rows x cols, leading dimension ld) viewed as
+// {8 rows, cols, rows/8}: MN-major operands take boxes {8,16,16}, K-major operands {8,128,2}.
+static bool encode_map(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj) {
+  if (!ctx->encode) return false;
+  cuuint64_t dims[3] = {8, (cuuint64_t)cols, (cuuint64_t)(rows / 8)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 8, 64};
+  cuuint32_t box[3] = {8, maj == MAJ_MN ? 16u : 128u, maj == MAJ_MN ? 16u : 2u};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool tma_ok(const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  return ((uintptr_t)ptr % 16 == 0) && (ld % 2 == 0) && (rows % 8 == 0) && rows >= 8 && cols >= 1 && rows < (1ll << 31) &&
+         cols < (1ll << 31) && ld * 8 < (1ll << 40);
+}
+
+template <int AMAJ, int BMAJ>
+static int launch_gemm_f64_tma(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB, const GemmF64Params& gp, cudaStream_t st) {
+  static bool configured[64] = {false};  // per device (one handle drives one device)
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_f64_tma_kernel<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  gemm_f64_tma_kernel<AMAJ, BMAJ><<<gp.tiles_m * gp.tiles_n, GF_THREADS, GF_SMEM_BYTES, st>>>(mA, mB, gp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+struct TmaMaps {
+  bool ok;
+  CUtensorMap mapT;  // triangular matrix A in the majorness its GEMM role needs
+  CUtensorMap mapV;  // B in the majorness its GEMM role needs
+};
+
+// One update  V[c-range] <- post*(beta*V[c-range] + sgn*Teff[c-range,k-range]*V[k-range])  for vectors [v0, v0+nv)
+template <typename T>
+static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+  const double sgn = P.solve ? -1.0 : 1.0;
+  const T* A = (const T*)P.A;
+  T* B = (T*)P.B;
+  if (std::is_same<T, double>::value && maps.ok) {
+    GemmF64Params gp{};
+    gp.beta = o.pre; gp.sgn = sgn; gp.post = o.post;
+    if (!P.right) {
+      // C = V[c-range, v-range] (cn x nv), A-operand = Teff block, B-operand = V[k-range, v-range] (K-major)
+      gp.M = (int)o.cn; gp.N = (int)nv; gp.K = (int)o.kn;
+      gp.a_mn0 = (int)o.c0; gp.a_k0 = (int)o.k0;
+      gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.k0;
+      gp.C = (double*)B + o.c0 + v0 * P.ldb; gp.ldc = P.ldb;
+      gp.tiles_m = (gp.M + GF_BM - 1) / GF_BM; gp.tiles_n = (gp.N + GF_BN - 1) / GF_BN;
+      if (!P.teff_trans) return launch_gemm_f64_tma<MAJ_MN, MAJ_K>(ctx, maps.mapT, maps.mapV, gp, st);
+      return launch_gemm_f64_tma<MAJ_K, MAJ_K>(ctx, maps.mapT, maps.mapV, gp, st);
+    } else {
+      // storage view: C = B[v-range, c-range] (nv x cn), A-operand = B[v-range, k-range] (MN-major),
+      // B-operand W(k,c) = Teff(c,k): teff_trans -> A[k,c] (K-major), else A[c,k] (N-major)
+      gp.M = (int)nv; gp.N = (int)o.cn; gp.K = (int)o.kn;
+      gp.a_mn0 = (int)v0; gp.a_k0 = (int)o.k0;
+      gp.b_mn0 = (int)o.c0; gp.b_k0 = (int)o.k0;
+      gp.C = (double*)B + v0 + o.c0 * P.ldb; gp.ldc = P.ldb;
+      gp.tiles_m = (gp.M + GF_BM - 1) / GF_BM; gp.tiles_n = (gp.N + GF_BN - 1) / GF_BN;
+      if (P.teff_trans) return launch_gemm_f64_tma<MAJ_MN, MAJ_K>(ctx, maps.mapV, maps.mapT, gp, st);
+      return launch_gemm_f64_tma<MAJ_MN, MAJ_MN>(ctx, maps.mapV, maps.mapT, gp, st);
+    }
+  }
+  // generic strided path
+  const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;   // Teff(r,k) strides
+  const T* Tblk = A + o.c0 * t_rs + o.k0 * t_cs;
+  if (!P.right) {
+    return launch_gemm_simt<T>(ctx, o.cn, nv, o.kn, Tblk, t_rs, t_cs, B + o.k0 + v0 * P.ldb, 1, P.ldb, B + o.c0 + v0 * P.ldb, P.ldb,
+                               o.pre, sgn, o.post, st);
+  }
+  // C(v,c) += sgn * sum_k B(v,k) * Teff(c,k)
+  return launch_gemm_simt<T>(ctx, nv, o.cn, o.kn, B + v0 + o.k0 * P.ldb, 1, P.ldb, Tblk, t_cs, t_rs, B + v0 + o.c0 * P.ldb, P.ldb, o.pre,
+                             sgn, o.post, st);
+}
+
+template <typename T>
+static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st) {
+  for (const Op& o : ops) {
+    int rc = (o.kind == Op::LEAF) ? launch_leaf<T>(ctx, P, o, v0, nv, st) : launch_update<T>(ctx, P, maps, o, v0, nv, st);
+    if (rc != NLA_OK) return rc;
+  }
+  return NLA_OK;
+}
+
+static int64_t default_leaf(int dtype) { (void)dtype; return LEAF_MAX; }
+
+template <typename T>
+static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream) {
+  int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
+  std::vector<Op> ops;
+  build_schedule(P, leaf, 0, P.n, false, true, ops);
+
+  TmaMaps maps{};
+  maps.ok = false;
+  if (std::is_same<T, double>::value && !ctx->force_simt && ops.size() > 1) {
+    const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
+    if (tma_ok(P.A, P.n, P.n, P.lda) && tma_ok(P.B, brows, bcols, P.ldb)) {
+      // majorness of each matrix in its GEMM role (see launch_update)
+      const int majT = !P.right ? (P.teff_trans ? MAJ_K : MAJ_MN) : (P.teff_trans ? MAJ_K : MAJ_MN);
+      const int majV = !P.right ? MAJ_K : MAJ_MN;
+      bool aligned = true;  // TMA coordinates are in blocks of 8; a K range may only be ragged at the matrix edge (zero fill)
+      for (const Op& o : ops)
+        if (o.kind == Op::GEMM && ((o.c0 % 8) || (o.k0 % 8) || ((o.kn % GF_BK) && (o.k0 + o.kn != P.n)))) aligned = false;
+      maps.ok = aligned && encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) &&
+                encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV);
+    }
+  }
+
+  // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
+  // small-K levels and the leaves of one slab overlap with the GEMMs of another.
+  int64_t S = std::max<int64_t>(1, ctx->nstreams);
+  const int64_t gran = 128;
+  if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
+  if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
+
+  while ((int64_t)ctx->streams.size() < S) {
+    cudaStream_t s; cudaEvent_t e;
+    NLA_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    NLA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->streams.push_back(s); ctx->events.push_back(e);
+  }
+  NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));
+  const int64_t per = ((P.m + S - 1) / S + gran - 1) / gran * gran;
+  for (int64_t s = 0; s < S; s++) {
+    const int64_t v0 = s * per, nv = std::min(per, P.m - v0);
+    if (nv <= 0) break;
+    NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[s], ctx->fork_event, 0));
+    int rc = run_ops<T>(ctx, P, maps, ops, v0, nv, ctx->streams[s]);
+    if (rc != NLA_OK) return rc;
+    NLA_CUDA(ctx, cudaEventRecord(ctx->events[s], ctx->streams[s]));
+    NLA_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->events[s], 0));
+  }
+  return NLA_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------------
+static inline bool valid(nla_handle_t h) { return h && h->magic == NLA_MAGIC; }
+
+static int make_problem(Problem& P, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                        const void* A, int64_t lda, void* B, int64_t ldb) {
+  if ((side != 'L' && side != 'R') || (uplo != 'L' && uplo != 'U') || (trans != 'N' && trans != 'T' && trans != 'C') ||
+      (func != 'S' && func != 'M'))
+    return NLA_ERR_INVALID_CHAR;
+  if (dtype != NLA_F64 && dtype != NLA_F32 && dtype != NLA_F16) return NLA_ERR_INVALID_DTYPE;
+  if (n < 0 || m < 0 || n >= (1ll << 31) || m >= (1ll << 31)) return NLA_ERR_INVALID_DIM;
+  const bool right = side == 'R';
+  if (lda < std::max<int64_t>(1, n) || ldb < std::max<int64_t>(1, right ? m : n)) return NLA_ERR_INVALID_DIM;
+  if (n > 0 && m > 0 && (!A || !B)) return NLA_ERR_NULL_POINTER;
+  P.dtype = dtype; P.solve = func == 'S'; P.right = right;
+  const bool tr = trans != 'N';
+  P.teff_trans = tr != right;
+  P.lower = (uplo == 'L') != P.teff_trans;
+  P.n = n; P.m = m; P.alpha = alpha; P.A = A; P.lda = lda; P.B = B; P.ldb = ldb;
+  P.es = right ? ldb : 1; P.vs = right ? 1 : ldb;
+  return NLA_OK;
+}
+
+static int dispatch(nla_context* ctx, const Problem& P, cudaStream_t st) {
+  switch (P.dtype) {
+    case NLA_F64: return rectrxm_typed<double>(ctx, P, st);
+    case NLA_F32: return rectrxm_typed<float>(ctx, P, st);
+    default: return rectrxm_typed<__half>(ctx, P, st);
+  }
+}
+
+extern "C" {
+
+int nla_version(void) { return 100; }
+
+const char* nla_status_string(int status) {
+  switch (status) {
+    case NLA_OK: return "ok";
+    case NLA_ERR_INVALID_CHAR: return "invalid side/uplo/trans/func character";
+    case NLA_ERR_INVALID_DIM: return "invalid dimension or leading dimension";
+    case NLA_ERR_INVALID_DTYPE: return "invalid dtype";
+    case NLA_ERR_NULL_POINTER: return "null pointer";
+    case NLA_ERR_CUDA: return "CUDA error (see nla_last_cuda_error)";
+    case NLA_ERR_NO_DEVICE: return "no CUDA device";
+    case NLA_ERR_UNSUPPORTED: return "unsupported";
+    case NLA_ERR_INVALID_HANDLE: return "invalid handle";
+  }
+  return "unknown status";
+}
+
+int nla_create(nla_handle_t* handle, int device) {
+  if (!handle) return NLA_ERR_NULL_POINTER;
+  *handle = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return NLA_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return NLA_ERR_NO_DEVICE;
+  nla_context* ctx = new (std::nothrow) nla_context();
+  if (!ctx) return NLA_ERR_UNSUPPORTED;
+  ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1;
+  ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
+  for (auto& s : ctx->host_streams) s = nullptr;
+  for (auto& e : ctx->host_events) e = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
+  cudaDriverEntryPointQueryResult qr;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+    ctx->encode = (EncodeTiledFn)fn;
+  if (cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
+  *handle = ctx;
+  return NLA_OK;
+}
+
+int nla_destroy(nla_handle_t h) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  cudaSetDevice(h->device);
+  for (auto s : h->streams) cudaStreamDestroy(s);
+  for (auto e : h->events) cudaEventDestroy(e);
+  cudaEventDestroy(h->fork_event);
+  for (auto s : h->host_streams) if (s) cudaStreamDestroy(s);
+  for (auto e : h->host_events) if (e) cudaEventDestroy(e);
+  if (h->stage_a) cudaFree(h->stage_a);
+  if (h->stage_b) cudaFree(h->stage_b);
+  h->magic = 0;
+  delete h;
+  return NLA_OK;
+}
+
+int nla_last_cuda_error(nla_handle_t h) { return valid(h) ? h->last_cuda : -1; }
+
+int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (!key) return NLA_ERR_NULL_POINTER;
+  if (!strcmp(key, "leaf")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->leaf = value; return NLA_OK; }
+  if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
+  if (!strcmp(key, "streams")) { if (value < 1 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
+  return NLA_ERR_UNSUPPORTED;
+}
+
+int64_t nla_get_option(nla_handle_t h, const char* key) {
+  if (!valid(h) || !key) return -1;
+  if (!strcmp(key, "leaf")) return h->leaf > 0 ? std::min<int64_t>(h->leaf, LEAF_MAX) : LEAF_MAX;
+  if (!strcmp(key, "force_simt")) return h->force_simt;
+  if (!strcmp(key, "streams")) return h->nstreams;
+  return -1;
+}
+
+int64_t nla_launch_count(nla_handle_t h, int reset) {
+  if (!valid(h)) return -1;
+  int64_t c = h->launches;
+  if (reset) h->launches = 0;
+  return c;
+}
+
+int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t* out, int64_t max_ops) {
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, NLA_F64, n, 1, 2.0, (const void*)8, std::max<int64_t>(1, n), (void*)8, std::max<int64_t>(1, n));
+  if (rc != NLA_OK) return -rc;
+  if (n == 0) return 0;
+  if (leaf <= 0) leaf = LEAF_MAX;
+  std::vector<Op> ops;
+  build_schedule(P, std::min<int64_t>(leaf, LEAF_MAX), 0, n, false, true, ops);
+  for (size_t i = 0; i < ops.size() && (int64_t)i < max_ops && out; i++) {
+    const Op& o = ops[i];
+    int64_t* r = out + 6 * i;
+    r[0] = o.kind == Op::GEMM;
+    r[1] = o.kind == Op::GEMM ? o.c0 : o.off; r[2] = o.kind == Op::GEMM ? o.cn : o.sz;
+    r[3] = o.kind == Op::GEMM ? o.k0 : 0; r[4] = o.kind == Op::GEMM ? o.kn : 0;
+    r[5] = (o.pre != 1.0) || (o.post != 1.0);
+  }
+  return (int64_t)ops.size();
+}
+
+int64_t nla_leaf_max(int dtype) { return (dtype >= 0 && dtype <= 2) ? LEAF_MAX : -1; }
+
+int nla_rectrxm(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                const void* A, int64_t lda, void* B, int64_t ldb, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A, lda, B, ldb);
+  if (rc != NLA_OK) return rc;
+  if (n == 0 || m == 0) return NLA_OK;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  return dispatch(h, P, (cudaStream_t)stream);
+}
+
+static int leaf_entry(nla_handle_t h, bool solve, char side, char uplo, int dtype, int64_t n, int64_t m, const void* A, int64_t lda,
+                      void* B, int64_t ldb, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  Problem P;
+  int rc = make_problem(P, side, uplo, 'N', solve ? 'S' : 'M', dtype, n, m, 1.0, A, lda, B, ldb);
+  if (rc != NLA_OK) return rc;
+  if (n > LEAF_MAX) return NLA_ERR_INVALID_DIM;
+  if (n == 0 || m == 0) return NLA_OK;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  Op o{};
+  o.kind = Op::LEAF; o.off = 0; o.sz = n; o.pre = 1.0; o.post = 1.0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case NLA_F64: return launch_leaf<double>(h, P, o, 0, m, st);
+    case NLA_F32: return launch_leaf<float>(h, P, o, 0, m, st);
+    default: return launch_leaf<__half>(h, P, o, 0, m, st);
+  }
+}
+
+int nla_trsm_leaf(nla_handle_t h, char side, char uplo, int dtype, int64_t n, int64_t m, const void* A, int64_t lda, void* B, int64_t ldb,
+                  void* stream) {
+  return leaf_entry(h, true, side, uplo, dtype, n, m, A, lda, B, ldb, stream);
+}
+int nla_trmm_leaf(nla_handle_t h, char side, char uplo, int dtype, int64_t n, int64_t m, const void* A, int64_t lda, void* B, int64_t ldb,
+                  void* stream) {
+  return leaf_entry(h, false, side, uplo, dtype, n, m, A, lda, B, ldb, stream);
+}
+
+}  // extern "C"
+
+template <typename T>
+static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int64_t N, int64_t K, int sign, const void* A, int64_t lda,
+                             const void* B, int64_t ldb, void* C, int64_t ldc, cudaStream_t st) {
+  const bool at = ta != 'N', bt = tb != 'N';
+  if (std::is_same<T, double>::value && !ctx->force_simt && !(at && bt)) {
+    // tensor-core path when both operands satisfy the TMA constraints
+    const int64_t ar = at ? K : M, ac = at ? M : K, br = bt ? N : K, bc = bt ? K : N;
+    if (tma_ok(A, ar, ac, lda) && tma_ok(B, br, bc, ldb)) {
+      CUtensorMap mA, mB;
+      const int majA = at ? MAJ_K : MAJ_MN, majB = bt ? MAJ_MN : MAJ_K;
+      if (encode_map(ctx, &mA, A, ar, ac, lda, majA) && encode_map(ctx, &mB, B, br, bc, ldb, majB)) {
+        GemmF64Params gp{};
+        gp.M = (int)M; gp.N = (int)N; gp.K = (int)K; gp.C = (double*)C; gp.ldc = ldc;
+        gp.beta = 1.0; gp.sgn = sign; gp.post = 1.0;
+        gp.tiles_m = (gp.M + GF_BM - 1) / GF_BM; gp.tiles_n = (gp.N + GF_BN - 1) / GF_BN;
+        if (!at && !bt) return launch_gemm_f64_tma<MAJ_MN, MAJ_K>(ctx, mA, mB, gp, st);
+        if (at && !bt) return launch_gemm_f64_tma<MAJ_K, MAJ_K>(ctx, mA, mB, gp, st);
+        return launch_gemm_f64_tma<MAJ_MN, MAJ_MN>(ctx, mA, mB, gp, st);
+      }
+    }
+  }
+  return launch_gemm_simt<T>(ctx, M, N, K, (const T*)A, at ? lda : 1, at ? 1 : lda, (const T*)B, bt ? ldb : 1, bt ? 1 : ldb, (T*)C, ldc,
+                             1.0, (double)sign, 1.0, st);
+}
+
+extern "C" {
+
+int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t M, int64_t N, int64_t K, int sign, const void* A,
+                    int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if ((transa != 'N' && transa != 'T' && transa != 'C') || (transb != 'N' && transb != 'T' && transb != 'C')) return NLA_ERR_INVALID_CHAR;
+  if (dtype != NLA_F64 && dtype != NLA_F32 && dtype != NLA_F16) return NLA_ERR_INVALID_DTYPE;
+  if (M < 0 || N < 0 || K < 0 || (sign != 1 && sign != -1)) return NLA_ERR_INVALID_DIM;
+  const int64_t ar = transa == 'N' ? M : K, br = transb == 'N' ? K : N;
+  if (lda < std::max<int64_t>(1, ar) || ldb < std::max<int64_t>(1, br) || ldc < std::max<int64_t>(1, M)) return NLA_ERR_INVALID_DIM;
+  if (M == 0 || N == 0 || K == 0) return NLA_OK;
+  if (!A || !B || !C) return NLA_ERR_NULL_POINTER;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case NLA_F64: return gemm_update_typed<double>(h, transa, transb, M, N, K, sign, A, lda, B, ldb, C, ldc, st);
+    case NLA_F32: return gemm_update_typed<float>(h, transa, transb, M, N, K, sign, A, lda, B, ldb, C, ldc, st);
+    default: return gemm_update_typed<__half>(h, transa, transb, M, N, K, sign, A, lda, B, ldb, C, ldc, st);
+  }
+}
+
+// Host-buffer entry point (round-1 version: stage, compute, copy back on one stream; slab pipelining is next).
+int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                     const void* A_host, int64_t lda, void* B_host, int64_t ldb) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A_host, lda, B_host, ldb);
+  if (rc != NLA_OK) return rc;
+  if (n == 0 || m == 0) return NLA_OK;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  const size_t es = dtype_size(dtype);
+  const int64_t bcols = P.right ? n : m;
+  const size_t a_bytes = (size_t)lda * n * es, b_bytes = (size_t)ldb * bcols * es;
+  if (h->stage_a_bytes < a_bytes) {
+    if (h->stage_a) cudaFree(h->stage_a);
+    h->stage_a = nullptr; h->stage_a_bytes = 0;
+    NLA_CUDA(h, cudaMalloc(&h->stage_a, a_bytes));
+    h->stage_a_bytes = a_bytes;
+  }
+  if (h->stage_b_bytes < b_bytes) {
+    if (h->stage_b) cudaFree(h->stage_b);
+    h->stage_b = nullptr; h->stage_b_bytes = 0;
+    NLA_CUDA(h, cudaMalloc(&h->stage_b, b_bytes));
+    h->stage_b_bytes = b_bytes;
+  }
+  if (!h->host_streams[0]) NLA_CUDA(h, cudaStreamCreateWithFlags(&h->host_streams[0], cudaStreamNonBlocking));
+  cudaStream_t st = h->host_streams[0];
+  NLA_CUDA(h, cudaMemcpyAsync(h->stage_a, A_host, a_bytes, cudaMemcpyHostToDevice, st));
+  NLA_CUDA(h, cudaMemcpyAsync(h->stage_b, B_host, b_bytes, cudaMemcpyHostToDevice, st));
+  P.A = h->stage_a; P.B = h->stage_b;
+  rc = dispatch(h, P, st);
+  if (rc != NLA_OK) return rc;
+  NLA_CUDA(h, cudaMemcpyAsync(B_host, h->stage_b, b_bytes, cudaMemcpyDeviceToHost, st));
+  NLA_CUDA(h, cudaStreamSynchronize(st));
+  return NLA_OK;
+}
+
+}  // extern "C"

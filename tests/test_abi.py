@@ -1,0 +1,120 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol declared in
+include/nextla_b200.h, reports errors as status codes, and its host-side schedule equals the reference's recursion."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import reference_port as rp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(nla):
+    lib = nla.load_library()
+    header = open(os.path.join(ROOT, "include", "nextla_b200.h")).read()
+    declared = set(re.findall(r"\b(nla_[a-z_0-9]+)\s*\(", header))
+    declared -= {"nla_context"}
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(nla.exported_symbols())
+    assert lib.nla_version() >= 100
+
+
+def test_status_strings_and_invalid_handle(nla):
+    lib = nla.load_library()
+    for code in range(0, 9):
+        assert lib.nla_status_string(code)
+    assert lib.nla_destroy(None) == 8
+    assert lib.nla_rectrxm(None, b"L", b"L", b"N", b"S", 0, 4, 4, 1.0, None, 4, None, 4, None) == 8
+    assert lib.nla_leaf_max(0) == 128 and lib.nla_leaf_max(7) == -1
+
+
+def test_create_without_gpu_fails_loudly(nla):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    rc = nla.load_library().nla_create(ctypes.byref(h), 0)
+    assert rc == 6 and not h.value  # NLA_ERR_NO_DEVICE: no CPU fallback
+    with pytest.raises(nla.NextLAError):
+        nla.Handle(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nextla.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("test oracle", "").replace("own oracle", ""), f"{f} mentions the oracle"
+
+
+def _reference_trace(side, uplo, trans, func, n, threshold):
+    """Run the oracle's restatement of unified_rec with recording stubs in place of the kernels and express every call
+    in the normalised coordinates the library's schedule uses."""
+    calls = []
+    A = np.zeros((n, n), order="F")
+    B = np.zeros((n, 1) if side == "L" else (1, n), order="F")
+    baseA, baseB = A.ctypes.data, B.ctypes.data
+
+    def boff(v):  # element offset of a view of B along the vector-element axis
+        return (v.ctypes.data - baseB) // 8
+
+    def leaf(Av, Bv):
+        calls.append((0, boff(Bv), Av.shape[0], 0, 0))
+
+    def mm(out, in1, in2, alpha):
+        if side == "L":   # out = rows c of B, in2 = rows k of B
+            calls.append((1, boff(out), out.shape[0], boff(in2), in2.shape[0]))
+        else:             # out = cols c of B, in1 = cols k of B
+            calls.append((1, boff(out), out.shape[1], boff(in1), in1.shape[1]))
+
+    saved = {k: getattr(rp, k) for k in ["left_lower_trsm", "left_upper_trsm", "right_lower_trsm", "right_upper_trsm", "left_lower_trmm",
+                                         "left_upper_trmm", "right_lower_trmm", "right_upper_trmm", "matmul_kernel"]}
+    try:
+        for k in saved:
+            setattr(rp, k, mm if k == "matmul_kernel" else leaf)
+        Av, u = (A.T, "U" if uplo == "L" else "L") if trans != "N" else (A, uplo)   # src/rectrxm.jl:56-59
+        rp.unified_rec(func, side, u, Av, n, B, threshold)
+    finally:
+        for k, v in saved.items():
+            setattr(rp, k, v)
+    return calls
+
+
+@pytest.mark.parametrize("n,leaf", [(16, 16), (64, 16), (100, 16), (300, 128), (1000, 64), (1024, 128), (777, 32)])
+def test_schedule_equals_reference_recursion(nla, n, leaf):
+    """The host-side schedule (flattened recursion) must issue the same leaves and updates in the same order as
+    unified_rec (src/rectrxm.jl:101-198) run with threshold = leaf, for every side/uplo/trans/func."""
+    import itertools
+
+    for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+        want = _reference_trace(side, uplo, trans, func, n, leaf)
+        got = [p[:5] for p in nla.plan(side, uplo, trans, func, n, leaf)]
+        assert got == want, (side, uplo, trans, func)
+
+
+def test_schedule_alpha_applied_exactly_once(nla):
+    """alpha is folded into kernels instead of the reference's full pass over B (src/rectrxm.jl:64,72): every element
+    range must be scaled by exactly one op."""
+    import itertools
+
+    for n, leaf in [(300, 128), (1024, 128), (100, 16)]:
+        for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+            cover = np.zeros(n, dtype=int)
+            for kind, c0, cn, k0, kn, carries in nla.plan(side, uplo, trans, func, n, leaf):
+                if carries:
+                    cover[c0:c0 + cn] += 1
+            assert (cover == 1).all(), (n, side, uplo, trans, func)
+
+
+def test_bad_arguments_return_status_codes(nla):
+    lib = nla.load_library()
+    assert lib.nla_plan(b"X", b"L", b"N", b"S", 8, 0, None, 0) == -1
+    assert lib.nla_plan(b"L", b"L", b"N", b"S", -1, 0, None, 0) == -2
+    assert lib.nla_plan(b"L", b"L", b"N", b"S", 0, 0, None, 0) == 0

@@ -1,0 +1,265 @@
+"""Parity tests proper: the CUDA library (through its C ABI) against the oracle (CPU restatement of the reference,
+oracle/) and against OpenBLAS trsm/trmm -- the reference's own test oracle (test/unified_rectrxm.jl:36-40).
+
+Tolerances (stated by BASELINE.json north_star, written here):
+  FP64: relative difference to BLAS < 1e-14 on the reference's grid (its own bar, test/unified_rectrxm.jl:8);
+        normwise backward error < 1e-13 elsewhere
+  FP32: < 1e-5 (test/trsm.jl:8)        FP16: backward error < 1e-2
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import c_port
+from oracle import reference_port as rp
+
+pytestmark = pytest.mark.gpu
+
+SIDES, UPLOS, TRANS, FUNCS = "LR", "LU", "NTC", "SM"
+
+
+def run_gpu(nla, side, uplo, trans, alpha, func, A, B0, ld_pad=0):
+    import torch
+
+    dA = nla.colmajor(A)
+    if ld_pad:
+        rows, cols = B0.shape
+        dB = nla.empty_colmajor(rows, cols, getattr(torch, str(B0.dtype)), ld=rows + ld_pad)
+        dB.copy_(torch.from_numpy(np.ascontiguousarray(B0)).cuda())
+        rowsA = A.shape[0]
+        dA2 = nla.empty_colmajor(rowsA, rowsA, getattr(torch, str(A.dtype)), ld=rowsA + ld_pad)
+        dA2.copy_(torch.from_numpy(np.ascontiguousarray(A)).cuda())
+        dA = dA2
+    else:
+        dB = nla.colmajor(B0)
+    nla.unified_rectrxm(side, uplo, trans, alpha, func, dA, dB)
+    torch.cuda.synchronize()
+    return nla.to_numpy(dB)
+
+
+def rel(a, b):
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("n", [16, 32, 128, 256])
+@pytest.mark.parametrize("m", [1, 8, 64])
+def test_reference_grid_fp64(nla, gpu, n, m):
+    """The reference's own test grid and criterion (test/unified_rectrxm.jl:10-44): FP64, alpha = 1, all
+    side/uplo/trans/func, relative error vs BLAS < 1e-14; additionally vs the oracle."""
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, TRANS, FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=1000 + n + m)
+        got = run_gpu(nla, side, uplo, trans, 1.0, func, A, B0)
+        blas = rp.blas_reference(side, uplo, trans, 1.0, func, A, B0)
+        want = c_port.unified_rectrxm(side, uplo, trans, 1.0, func, A, B0.copy(order="F"))
+        assert rel(got, blas) < 1e-14, (side, uplo, trans, func)
+        assert rel(got, want) < 1e-14, (side, uplo, trans, func)
+
+
+@pytest.mark.parametrize("n,m", [(300, 40), (512, 256), (1000, 72), (1024, 1024), (1536, 130), (2048, 512)])
+@pytest.mark.parametrize("alpha", [1.0, -0.5])
+def test_recursive_fp64_all_variants(nla, gpu, n, m, alpha):
+    """n > leaf: recursion + GEMM updates (tensor-core path when TMA-eligible, generic path otherwise),
+    non power-of-two n, alpha != 1 -- everything the reference's tests leave unpinned."""
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=n + m)
+        got = run_gpu(nla, side, uplo, trans, alpha, func, A, B0)
+        want = c_port.unified_rectrxm(side, uplo, trans, alpha, func, A, B0.copy(order="F"))
+        blas = rp.blas_reference(side, uplo, trans, alpha, func, A, B0)
+        err = rp.error_metric(side, uplo, trans, alpha, func, A, B0, got)
+        assert err < 1e-13, (side, uplo, trans, func, err)
+        assert rel(got, blas) < 1e-13, (side, uplo, trans, func)
+        assert rel(got, want) < 1e-13, (side, uplo, trans, func)
+
+
+@pytest.mark.parametrize("n,m,pad", [(257, 33, 0), (640, 200, 3), (1024, 512, 1), (1024, 512, 2)])
+def test_unaligned_and_padded_ld_fp64(nla, gpu, n, m, pad):
+    """Odd sizes / odd leading dimensions force the generic GEMM path; an even pad keeps the TMA path with ld > rows."""
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=5 * n + m)
+        got = run_gpu(nla, side, uplo, trans, 2.0, func, A, B0, ld_pad=pad)
+        blas = rp.blas_reference(side, uplo, trans, 2.0, func, A, B0)
+        assert rel(got, blas) < 1e-13, (side, uplo, trans, func)
+
+
+def test_force_simt_matches_tensor_path(nla, gpu):
+    n, m = 1024, 384
+    A, B0 = rp.make_inputs(n, m, "L", "L", np.float64, seed=3, recipe="scaled")
+    a = run_gpu(nla, "L", "L", "N", 1.0, "S", A, B0)
+    gpu.set_option("force_simt", 1)
+    try:
+        b = run_gpu(nla, "L", "L", "N", 1.0, "S", A, B0)
+    finally:
+        gpu.set_option("force_simt", 0)
+    assert rel(a, b) < 1e-13
+
+
+@pytest.mark.parametrize("streams", [2, 4])
+def test_concurrent_rhs_slabs(nla, gpu, streams):
+    n, m = 1024, 1100
+    gpu.set_option("streams", streams)
+    try:
+        for side, func in itertools.product(SIDES, FUNCS):
+            A, B0 = rp.make_inputs(n, m, side, "L", np.float64, seed=11)
+            got = run_gpu(nla, side, "L", "N", 1.5, func, A, B0)
+            blas = rp.blas_reference(side, "L", "N", 1.5, func, A, B0)
+            assert rel(got, blas) < 1e-13
+    finally:
+        gpu.set_option("streams", 1)
+
+
+@pytest.mark.parametrize("leaf", [16, 32, 64, 128])
+def test_leaf_cutoff_option(nla, gpu, leaf):
+    gpu.set_option("leaf", leaf)
+    try:
+        for side, uplo, func in itertools.product(SIDES, UPLOS, FUNCS):
+            A, B0 = rp.make_inputs(520, 96, side, uplo, np.float64, seed=leaf)
+            got = run_gpu(nla, side, uplo, "N", 1.0, func, A, B0)
+            blas = rp.blas_reference(side, uplo, "N", 1.0, func, A, B0)
+            assert rel(got, blas) < 1e-13
+    finally:
+        gpu.set_option("leaf", 0)
+
+
+def test_opposite_triangle_never_read(nla, gpu):
+    """Fill the unreferenced triangle of A with NaN: the result must be unchanged (only `uplo` is read)."""
+    n, m = 640, 136
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=17)
+        An = A.copy(order="F")
+        idx = np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)
+        An[idx] = np.nan
+        got = run_gpu(nla, side, uplo, trans, 1.0, func, An, B0)
+        blas = rp.blas_reference(side, uplo, trans, 1.0, func, A, B0)
+        assert np.isfinite(got).all() and rel(got, blas) < 1e-13, (side, uplo, trans, func)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float16, 1e-2)])
+@pytest.mark.parametrize("n,m", [(16, 8), (128, 64), (256, 64), (700, 96), (1024, 256)])
+def test_low_precision(nla, gpu, dtype, tol, n, m):
+    """Float32 (reference tolerance 1e-5, test/trsm.jl:8) and Float16 (1e-2 backward error, FP64 truth on the rounded inputs)."""
+    recipe = "scaled" if dtype == np.float16 else "reference"
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=n + 3 * m, recipe=recipe)
+        got = run_gpu(nla, side, uplo, trans, 1.0, func, A, B0)
+        err = rp.error_metric(side, uplo, trans, 1.0, func, A, B0, got)
+        truth = rp.blas_reference(side, uplo, trans, 1.0, func, A, B0)
+        assert err < tol, (side, uplo, trans, func, err)
+        assert rel(got, truth) < (1e-5 if dtype == np.float32 else 1e-2), (side, uplo, trans, func)
+
+
+def test_leaf_entry_points_fp32(nla, gpu):
+    """test/trsm.jl:10-64: the four TRSM leaves in Float32, n in {16,32,128}, m in {1,8,64}, tolerance 1e-5 vs BLAS;
+    plus the four TRMM leaves (untested upstream)."""
+    import torch
+
+    fns = {("L", "L"): (nla.LeftLowerTRSM, nla.LeftLowerTRMM), ("L", "U"): (nla.LeftUpperTRSM, nla.LeftUpperTRMM),
+           ("R", "L"): (nla.RightLowerTRSM, nla.RightLowerTRMM), ("R", "U"): (nla.RightUpperTRSM, nla.RightUpperTRMM)}
+    for n, m in itertools.product([16, 32, 128], [1, 8, 64]):
+        for (side, uplo), (fs, fm) in fns.items():
+            A, B0 = rp.make_inputs(n, m, side, uplo, np.float32, seed=n * m)
+            for f, func in ((fs, "S"), (fm, "M")):
+                dA, dB = nla.colmajor(A), nla.colmajor(B0)
+                f(dA, dB)
+                torch.cuda.synchronize()
+                blas = rp.blas_reference(side, uplo, "N", 1.0, func, A, B0)
+                assert rel(nla.to_numpy(dB), blas) < 1e-5, (n, m, side, uplo, func)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-14), (np.float32, 1e-5)])
+def test_gemm_add_sub(nla, gpu, dtype, tol):
+    """GEMM_ADD!(A,B,C): C += A*B and GEMM_SUB!(A,B,C): A -= B*C (src/matmul.jl:69-81), incl. transposed operands."""
+    import torch
+
+    rng = np.random.RandomState(0)
+    for (M, N, K) in [(128, 128, 128), (256, 384, 512), (100, 36, 77), (1024, 640, 256)]:
+        A = np.asfortranarray(rng.rand(M, K).astype(dtype)); B = np.asfortranarray(rng.rand(K, N).astype(dtype))
+        C = np.asfortranarray(rng.rand(M, N).astype(dtype))
+        dA, dB, dC = nla.colmajor(A), nla.colmajor(B), nla.colmajor(C)
+        nla.GEMM_ADD(dA, dB, dC); torch.cuda.synchronize()
+        want = C.astype(np.float64) + A.astype(np.float64) @ B.astype(np.float64)
+        assert rel(nla.to_numpy(dC), want) < tol
+        dC = nla.colmajor(C)
+        nla.GEMM_SUB(dC, dA, dB); torch.cuda.synchronize()
+        want = C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)
+        assert rel(nla.to_numpy(dC), want) < tol
+        At = np.asfortranarray(A.T.copy()); Bt = np.asfortranarray(B.T.copy())
+        dC = nla.colmajor(C)
+        nla.GEMM_ADD(nla.colmajor(At), dB, dC, transa="T"); torch.cuda.synchronize()
+        want = C.astype(np.float64) + A.astype(np.float64) @ B.astype(np.float64)
+        assert rel(nla.to_numpy(dC), want) < tol
+        dC = nla.colmajor(C)
+        nla.GEMM_ADD(dA, nla.colmajor(Bt), dC, transb="T"); torch.cuda.synchronize()
+        assert rel(nla.to_numpy(dC), want) < tol
+
+
+def test_edge_cases_and_errors(nla, gpu):
+    import torch
+
+    # empty problems are quick returns
+    A = nla.colmajor(np.zeros((0, 0))); B = nla.colmajor(np.zeros((0, 5)))
+    nla.unified_rectrxm("L", "L", "N", 1.0, "S", A, B)
+    A1, B1 = rp.make_inputs(1, 3, "L", "L", np.float64, seed=1)
+    got = run_gpu(nla, "L", "L", "N", 3.0, "S", A1, B1)
+    assert np.allclose(got, 3.0 * B1 / A1[0, 0])
+    A, B0 = rp.make_inputs(64, 8, "L", "L", np.float64, seed=2)
+    dA, dB = nla.colmajor(A), nla.colmajor(B0)
+    for bad in [("X", "L", "N", "S"), ("L", "X", "N", "S"), ("L", "L", "X", "S"), ("L", "L", "N", "X")]:
+        with pytest.raises(nla.NextLAError):
+            nla.unified_rectrxm(bad[0], bad[1], bad[2], 1.0, bad[3], dA, dB)
+    with pytest.raises(nla.NextLAError):
+        nla.unified_rectrxm("L", "L", "N", 1.0, "S", dA, nla.colmajor(np.zeros((32, 8))))
+    with pytest.raises(nla.NextLAError):
+        nla.unified_rectrxm("L", "L", "N", 1.0, "S", torch.zeros(4, 4, dtype=torch.float64), torch.zeros(4, 4, dtype=torch.float64))
+
+
+def test_host_buffer_entry_point(nla, gpu):
+    n, m = 768, 200
+    for side, func in itertools.product(SIDES, FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, "U", np.float64, seed=23)
+        B = B0.copy(order="F")
+        nla.unified_rectrxm_host(side, "U", "T", 0.75, func, A, B)
+        blas = rp.blas_reference(side, "U", "T", 0.75, func, A, B0)
+        assert rel(B, blas) < 1e-13
+
+
+def _gpu_backward_error(torch, side, uplo, trans, alpha, func, dA, dB0, dX):
+    T = torch.tril(dA) if uplo == "L" else torch.triu(dA)
+    if trans != "N":
+        T = T.t()
+    nA = torch.linalg.norm(T)
+    if func == "S":
+        R = (T @ dX if side == "L" else dX @ T) - alpha * dB0
+        return (torch.linalg.norm(R) / (nA * torch.linalg.norm(dX) + abs(alpha) * torch.linalg.norm(dB0))).item()
+    Pm = alpha * (T @ dB0 if side == "L" else dB0 @ T)
+    return (torch.linalg.norm(dX - Pm) / (abs(alpha) * nA * torch.linalg.norm(dB0))).item()
+
+
+@pytest.mark.parametrize("side,uplo,trans,func", [("L", "L", "N", "S"), ("L", "U", "T", "M"), ("R", "L", "N", "S"), ("R", "U", "T", "M"), ("L", "L", "N", "M")])
+def test_large_size_properties_fp64(nla, gpu, side, uplo, trans, func):
+    """At a BASELINE-scale size (n = m = 8192; the oracle would take minutes) use size-independent properties:
+    backward error (computed on the GPU in FP64 by an independent cuBLAS product), linearity in the right-hand
+    sides, and the solve/multiply round trip  M(S(B)) == B."""
+    import torch
+
+    n = m = 8192
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    A = (2 * torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g) - 1) / n ** 0.5
+    A = (torch.tril(A, -1) if uplo == "L" else torch.triu(A, 1)) + torch.diag(1 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g))
+    dA = A.t().contiguous().t()
+    shape = (n, m)
+    B0 = (torch.rand(shape, dtype=torch.float64, device="cuda", generator=g) + 1).t().contiguous().t()
+    X = B0.clone(memory_format=torch.preserve_format)
+    assert X.stride(0) == 1
+    nla.unified_rectrxm(side, uplo, trans, 1.25, func, dA, X)
+    err = _gpu_backward_error(torch, side, uplo, trans, 1.25, func, dA, B0, X)
+    assert err < 1e-13, err
+    # linearity: op(2*B) == 2*op(B) exactly (power-of-two scaling commutes with rounding)
+    X2 = (2 * B0).t().contiguous().t()
+    nla.unified_rectrxm(side, uplo, trans, 1.25, func, dA, X2)
+    assert torch.equal(X2, 2 * X)
+    # round trip with the inverse operation
+    inv = "M" if func == "S" else "S"
+    nla.unified_rectrxm(side, uplo, trans, 1 / 1.25, inv, dA, X)
+    assert (torch.linalg.norm(X - B0) / torch.linalg.norm(B0)).item() < 1e-11

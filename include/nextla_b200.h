@@ -70,7 +70,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
 /* Tunables (the reference hard-codes its thresholds, src/rectrxm.jl:52,63).  Keys:
  *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
- *   "streams"     number of RHS slabs run on concurrent streams (default 1)                         */
+ *   "streams"     number of RHS slabs run on concurrent streams (default 1)
+ *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
 int64_t nla_get_option(nla_handle_t handle, const char *key);
 
@@ -79,6 +80,11 @@ int64_t nla_get_option(nla_handle_t handle, const char *key);
  * normalised coordinates of DESIGN.md (leaf: diagonal block [c0, c0+cn); update: V[c0:c0+cn] +-= Teff[c,k] V[k0:k0+kn]).
  * Returns the number of ops (may exceed max_ops) or a negative nla_status.  Needs no GPU. */
 int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t *ops, int64_t max_ops);
+
+/* Per-launch device times recorded while option "profile" is 1: waits for the recorded work, writes up to max_records
+ * records of 3 doubles {kind (0 = leaf, 1 = GEMM update), algorithmic flops of the launch, milliseconds} in launch order,
+ * clears the log and returns the number of records that were available (or a negative nla_status). */
+int64_t nla_profile_read(nla_handle_t handle, double *records, int64_t max_records);
 
 /* Counters for bench.py: kernels launched by this handle since the last reset. */
 int64_t nla_launch_count(nla_handle_t handle, int reset);

@@ -61,6 +61,7 @@ def load_library():
         "nla_set_option": (I, [H, c.c_char_p, L]),
         "nla_get_option": (L, [H, c.c_char_p]),
         "nla_launch_count": (L, [H, I]),
+        "nla_profile_read": (L, [H, c.POINTER(c.c_double), L]),
         "nla_plan": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
     }
     for name, (res, args) in protos.items():
@@ -72,7 +73,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan"]
+            "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 
 def _check(rc: int, h=None):
@@ -101,6 +102,15 @@ class Handle:
 
     def launch_count(self, reset: bool = False) -> int:
         return int(load_library().nla_launch_count(self._h, 1 if reset else 0))
+
+    def profile_read(self, max_records: int = 1 << 16):
+        """[(kind, flops, ms)] for every launch since option "profile" was set / the last read (kind 0 = leaf, 1 = GEMM update)."""
+        buf = (ctypes.c_double * (3 * max_records))()
+        n = load_library().nla_profile_read(self._h, buf, max_records)
+        if n < 0:
+            _check(-n, self._h)
+        n = min(n, max_records)
+        return [(int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
 
     def close(self):
         if self._h:

@@ -28,6 +28,10 @@ struct nla_context {
   int64_t leaf;         // recursion cutoff (0 = default)
   int64_t force_simt;
   int64_t nstreams;
+  int64_t profile;
+  struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> prof_pool;
   // helper streams / events for concurrent RHS slabs
   std::vector<cudaStream_t> streams;
   std::vector<cudaEvent_t> events;
@@ -250,8 +254,21 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
 template <typename T>
 static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st) {
   for (const Op& o : ops) {
+    nla_context::ProfRec pr{};
+    if (ctx->profile) {
+      for (cudaEvent_t* e : {&pr.e0, &pr.e1}) {
+        if (ctx->prof_pool.empty()) { NLA_CUDA(ctx, cudaEventCreate(e)); } else { *e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+      }
+      pr.kind = o.kind == Op::GEMM;
+      pr.flops = o.kind == Op::GEMM ? 2.0 * (double)o.cn * (double)o.kn * (double)nv : (double)o.sz * (double)o.sz * (double)nv;
+      NLA_CUDA(ctx, cudaEventRecord(pr.e0, st));
+    }
     int rc = (o.kind == Op::LEAF) ? launch_leaf<T>(ctx, P, o, v0, nv, st) : launch_update<T>(ctx, P, maps, o, v0, nv, st);
     if (rc != NLA_OK) return rc;
+    if (ctx->profile) {
+      NLA_CUDA(ctx, cudaEventRecord(pr.e1, st));
+      ctx->prof.push_back(pr);
+    }
   }
   return NLA_OK;
 }
@@ -367,7 +384,7 @@ int nla_create(nla_handle_t* handle, int device) {
   nla_context* ctx = new (std::nothrow) nla_context();
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
-  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1; ctx->profile = 0;
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -386,6 +403,8 @@ int nla_destroy(nla_handle_t h) {
   cudaSetDevice(h->device);
   for (auto s : h->streams) cudaStreamDestroy(s);
   for (auto e : h->events) cudaEventDestroy(e);
+  for (auto& pr : h->prof) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
+  for (auto e : h->prof_pool) cudaEventDestroy(e);
   cudaEventDestroy(h->fork_event);
   for (auto s : h->host_streams) if (s) cudaStreamDestroy(s);
   for (auto e : h->host_events) if (e) cudaEventDestroy(e);
@@ -403,6 +422,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!key) return NLA_ERR_NULL_POINTER;
   if (!strcmp(key, "leaf")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->leaf = value; return NLA_OK; }
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
+  if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 1 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
   return NLA_ERR_UNSUPPORTED;
 }
@@ -412,7 +432,24 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "leaf")) return h->leaf > 0 ? std::min<int64_t>(h->leaf, LEAF_MAX) : LEAF_MAX;
   if (!strcmp(key, "force_simt")) return h->force_simt;
   if (!strcmp(key, "streams")) return h->nstreams;
+  if (!strcmp(key, "profile")) return h->profile;
   return -1;
+}
+
+int64_t nla_profile_read(nla_handle_t h, double* records, int64_t max_records) {
+  if (!valid(h)) return -NLA_ERR_INVALID_HANDLE;
+  const int64_t n = (int64_t)h->prof.size();
+  for (int64_t i = 0; i < n; i++) {
+    auto& pr = h->prof[i];
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(pr.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.e0, pr.e1);
+    if (e != cudaSuccess) { h->last_cuda = (int)e; return -NLA_ERR_CUDA; }
+    if (records && i < max_records) { records[3 * i] = pr.kind; records[3 * i + 1] = pr.flops; records[3 * i + 2] = ms; }
+    h->prof_pool.push_back(pr.e0); h->prof_pool.push_back(pr.e1);
+  }
+  h->prof.clear();
+  return n;
 }
 
 int64_t nla_launch_count(nla_handle_t h, int reset) {

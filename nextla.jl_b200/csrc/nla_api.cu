@@ -11,6 +11,7 @@
 #include "gemm_f64.cuh"
 #include "gemm_simt.cuh"
 #include "leaf.cuh"
+#include "slab_f64.cuh"
 
 using namespace nla;
 
@@ -29,6 +30,7 @@ struct nla_context {
   int64_t force_simt;
   int64_t nstreams;
   int64_t profile;
+  int64_t macro;        // order of the diagonal blocks handled by the fused slab kernel (0 = disabled)
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
@@ -203,8 +205,23 @@ static int launch_gemm_f64_tma(nla_context* ctx, const CUtensorMap& mA, const CU
   return NLA_OK;
 }
 
+template <int AMAJ, bool LOWER, bool SOLVE>
+static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV, const SlabParams& sp, cudaStream_t st) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(slab_f64_kernel<AMAJ, LOWER, SOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  const unsigned grid = (unsigned)((sp.v_count + SL_W - 1) / SL_W);
+  slab_f64_kernel<AMAJ, LOWER, SOLVE><<<grid, SL_THREADS, SL_SMEM_BYTES, st>>>(mT, mV, sp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
 struct TmaMaps {
   bool ok;
+  bool fused;        // diagonal blocks go to the fused slab kernel (left side, FP64, TMA-eligible)
   CUtensorMap mapT;  // triangular matrix A in the majorness its GEMM role needs
   CUtensorMap mapV;  // B in the majorness its GEMM role needs
 };
@@ -251,6 +268,26 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
                              sgn, o.post, st);
 }
 
+// Fused macro-leaf for a LEAF op (left side, FP64): see slab_f64.cuh
+static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+  SlabParams sp{};
+  sp.T = (int)o.sz; sp.off = (int)o.off; sp.v_base = (int)v0; sp.v_count = (int)nv;
+  sp.A = (const double*)P.A;
+  sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
+  sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = o.pre; sp.post = o.post;
+  const int v = (P.teff_trans ? 4 : 0) | (P.lower ? 2 : 0) | (P.solve ? 1 : 0);
+  switch (v) {
+    case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 1: return launch_slab_variant<MAJ_MN, false, true>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 2: return launch_slab_variant<MAJ_MN, true, false>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 3: return launch_slab_variant<MAJ_MN, true, true>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 4: return launch_slab_variant<MAJ_K, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 5: return launch_slab_variant<MAJ_K, false, true>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 6: return launch_slab_variant<MAJ_K, true, false>(ctx, maps.mapT, maps.mapV, sp, st);
+    default: return launch_slab_variant<MAJ_K, true, true>(ctx, maps.mapT, maps.mapV, sp, st);
+  }
+}
+
 template <typename T>
 static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st) {
   for (const Op& o : ops) {
@@ -263,7 +300,10 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
       pr.flops = o.kind == Op::GEMM ? 2.0 * (double)o.cn * (double)o.kn * (double)nv : (double)o.sz * (double)o.sz * (double)nv;
       NLA_CUDA(ctx, cudaEventRecord(pr.e0, st));
     }
-    int rc = (o.kind == Op::LEAF) ? launch_leaf<T>(ctx, P, o, v0, nv, st) : launch_update<T>(ctx, P, maps, o, v0, nv, st);
+    int rc;
+    if (o.kind == Op::GEMM) rc = launch_update<T>(ctx, P, maps, o, v0, nv, st);
+    else if (maps.fused) rc = launch_slab(ctx, P, maps, o, v0, nv, st);
+    else rc = launch_leaf<T>(ctx, P, o, v0, nv, st);
     if (rc != NLA_OK) return rc;
     if (ctx->profile) {
       NLA_CUDA(ctx, cudaEventRecord(pr.e1, st));
@@ -277,24 +317,41 @@ static int64_t default_leaf(int dtype) { (void)dtype; return LEAF_MAX; }
 
 template <typename T>
 static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream) {
-  int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
+  const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
   std::vector<Op> ops;
-  build_schedule(P, leaf, 0, P.n, false, true, ops);
-
   TmaMaps maps{};
-  maps.ok = false;
-  if (std::is_same<T, double>::value && !ctx->force_simt && ops.size() > 1) {
-    const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
-    if (tma_ok(P.A, P.n, P.n, P.lda) && tma_ok(P.B, brows, bcols, P.ldb)) {
-      // majorness of each matrix in its GEMM role (see launch_update)
-      const int majT = !P.right ? (P.teff_trans ? MAJ_K : MAJ_MN) : (P.teff_trans ? MAJ_K : MAJ_MN);
-      const int majV = !P.right ? MAJ_K : MAJ_MN;
-      bool aligned = true;  // TMA coordinates are in blocks of 8; a K range may only be ragged at the matrix edge (zero fill)
+  maps.ok = false; maps.fused = false;
+
+  // FP64 tensor-core path: both matrices must satisfy the TMA constraints (16-byte aligned base, even leading dimension,
+  // row counts that are multiples of 8); otherwise the generic strided kernels take the call.
+  const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
+  const bool tma = std::is_same<T, double>::value && !ctx->force_simt && ctx->encode && tma_ok(P.A, P.n, P.n, P.lda) &&
+                   tma_ok(P.B, brows, bcols, P.ldb);
+  auto gemm_aligned = [&]() {  // TMA coordinates are in blocks of 8; a K range may only be ragged at the matrix edge (zero fill)
+    for (const Op& o : ops)
+      if (o.kind == Op::GEMM && ((o.c0 % 8) || (o.k0 % 8) || ((o.kn % GF_BK) && (o.k0 + o.kn != P.n)))) return false;
+    return true;
+  };
+  if (tma) {
+    const int majT = P.teff_trans ? MAJ_K : MAJ_MN;      // majorness of each matrix in its GEMM role (see launch_update)
+    const int majV = !P.right ? MAJ_K : MAJ_MN;
+    if (!P.right && ctx->macro >= 8) {
+      // left side: diagonal blocks of order <= macro go to the fused slab kernel
+      build_schedule(P, ctx->macro, 0, P.n, false, true, ops);
+      bool ok = gemm_aligned();
       for (const Op& o : ops)
-        if (o.kind == Op::GEMM && ((o.c0 % 8) || (o.k0 % 8) || ((o.kn % GF_BK) && (o.k0 + o.kn != P.n)))) aligned = false;
-      maps.ok = aligned && encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) &&
-                encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV);
+        if (o.kind == Op::LEAF && ((o.off % 8) || ((o.sz % SL_BM) && (o.off + o.sz != P.n)))) ok = false;
+      if (ok) maps.fused = maps.ok = encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) &&
+                                     encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV);
+      if (!maps.ok) ops.clear();
     }
+    if (!maps.ok) {
+      build_schedule(P, leaf, 0, P.n, false, true, ops);
+      if (ops.size() > 1 && gemm_aligned())
+        maps.ok = encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) && encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV);
+    }
+  } else {
+    build_schedule(P, leaf, 0, P.n, false, true, ops);
   }
 
   // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
@@ -384,7 +441,7 @@ int nla_create(nla_handle_t* handle, int device) {
   nla_context* ctx = new (std::nothrow) nla_context();
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
-  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1; ctx->profile = 0;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1; ctx->profile = 0; ctx->macro = 1024;
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -423,6 +480,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "leaf")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->leaf = value; return NLA_OK; }
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
+  if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 1 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
   return NLA_ERR_UNSUPPORTED;
 }
@@ -433,6 +491,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "force_simt")) return h->force_simt;
   if (!strcmp(key, "streams")) return h->nstreams;
   if (!strcmp(key, "profile")) return h->profile;
+  if (!strcmp(key, "macro")) return h->macro;
   return -1;
 }
 

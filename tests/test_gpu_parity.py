@@ -109,6 +109,23 @@ def test_concurrent_rhs_slabs(nla, gpu, streams):
         gpu.set_option("streams", 1)
 
 
+@pytest.mark.parametrize("macro", [0, 128, 256, 512, 4096])
+def test_fused_slab_cutoff_option(nla, gpu, macro):
+    """`macro` = order of the diagonal blocks handled by the fused slab kernel (0 = recursion down to the 128 leaf;
+    >= n = the whole problem in one launch).  Ragged n (multiple of 8 but not of 128) and ragged m included."""
+    gpu.set_option("macro", macro)
+    try:
+        for n, m in [(1024, 256), (1160, 200), (2048 + 72, 136)]:
+            for uplo, trans, func in itertools.product(UPLOS, "NT", FUNCS):
+                A, B0 = rp.make_inputs(n, m, "L", uplo, np.float64, seed=n + macro)
+                got = run_gpu(nla, "L", uplo, trans, -1.5, func, A, B0)
+                blas = rp.blas_reference("L", uplo, trans, -1.5, func, A, B0)
+                err = rp.error_metric("L", uplo, trans, -1.5, func, A, B0, got)
+                assert rel(got, blas) < 1e-13 and err < 1e-14, (n, m, uplo, trans, func, rel(got, blas), err)
+    finally:
+        gpu.set_option("macro", 1024)
+
+
 @pytest.mark.parametrize("leaf", [16, 32, 64, 128])
 def test_leaf_cutoff_option(nla, gpu, leaf):
     gpu.set_option("leaf", leaf)

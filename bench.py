@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--m", type=int, default=M_PER_GPU, help="override RHS per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("NLA_STREAMS", "1")))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("NLA_STREAMS", "0")), help="0 = library default")
     return ap.parse_args()
 
 
@@ -187,7 +187,6 @@ def main():
     if rank == 0:
         sampler.start()
     h.launch_count(reset=True)
-    h.set_option("profile", 1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
     t_wall0 = time.perf_counter()
@@ -200,8 +199,18 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     launches = h.launch_count()
+    # per-launch device times for the roofline: two extra steps right after the timed region with the RHS slabs serialised on
+    # one stream (with concurrent slabs the per-launch event intervals would overlap and over-count)
+    h.set_option("streams", 1)
+    h.set_option("profile", 1)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        X.copy_(B0)
+        nla.unified_rectrxm("L", "L", "N", 1.0, "S", A, X, handle=h)
+    torch.cuda.synchronize()
     prof = h.profile_read()
     h.set_option("profile", 0)
+    h.set_option("streams", args.streams)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -222,14 +231,16 @@ def main():
     l_fl, l_ms = sum(f for f, _ in leafs), sum(ms for _, ms in leafs)
     top = max(gemm, key=lambda r: r[0]) if gemm else (0.0, 1.0)
     achieved = g_fl / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (FP64 DMMA update, all recursion levels)", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+    roofline = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (FP64 DMMA update, recursion levels above the fused-slab cutoff)", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
                 "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": GEMM_TRAFFIC_BYTES,
                 "peak_source": "measured DMMA.8x8x4 issue-rate probe on this pool (profiles/r01_probe_dmma_peak.txt); MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2; cuBLAS DGEMM measured 35.4",
-                "launches_per_step": len(gemm) // max(1, args.steps), "avg_launch_ms": g_ms / max(1, len(gemm)),
-                "flops_per_step": g_fl / max(1, args.steps),
+                "launches_per_step": len(gemm) // prof_steps, "avg_launch_ms": g_ms / max(1, len(gemm)),
+                "flops_per_step": g_fl / prof_steps,
+                "how": "algorithmic flops of all GEMM-update launches / their CUDA-event durations, 2 profiled steps run right after the timed region on one stream",
                 "top_level_launch": {"flops": top[0], "ms": top[1], "tflops": top[0] / (top[1] * 1e-3) * 1e-12},
-                "gemm_share_of_step": g_ms / max(1e-9, sum(step_ms)), "leaf_share_of_step": l_ms / max(1e-9, sum(step_ms)),
+                "gemm_share_of_step": g_ms / max(1e-9, g_ms + l_ms), "leaf_share_of_step": l_ms / max(1e-9, g_ms + l_ms),
+                "fused_slab_launches_per_step": len(leafs) // prof_steps,
                 "leaf_tflops": l_fl / (l_ms * 1e-3) * 1e-12 if l_ms > 0 else None,
                 "whole_step_frac_of_peak": value / world / FP64_PEAK_TFLOPS}
 
@@ -285,11 +296,11 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cn = 4096
+        cn = 8192
         sec, cores = cpu_port_time(cn, cn)
         cpu = {"value": float(cn) ** 3 / sec * 1e-12, "unit": UNIT, "cores": cores, "kind": "port", "seconds": sec,
                "sample": f"oracle/nla_oracle.c (C/OpenMP restatement of the reference algorithm; Julia unavailable), FP64 L/L/N TRSM n=m={cn} "
-                         f"(1/64 of the headline flops), {cores} OpenMP threads"}
+                         f"(1/8 of the headline flops), {cores} OpenMP threads"}
         try:
             from scipy.linalg import blas
             from oracle import reference_port as rp
@@ -298,6 +309,7 @@ def main():
             t0 = time.perf_counter()
             blas.dtrsm(1.0, Ah, Bh, side=0, lower=1, trans_a=0, diag=0)
             cpu["openblas_dtrsm_tflops"] = float(cn) ** 3 / (time.perf_counter() - t0) * 1e-12
+            cpu["openblas_note"] = "scipy.linalg.blas.dtrsm (OpenBLAS, the reference tests' own oracle) on the same sample, all cores"
         except Exception as e:  # noqa: BLE001
             cpu["openblas_dtrsm_tflops"] = f"unavailable: {e}"
 
@@ -308,7 +320,7 @@ def main():
                            "n": n, "rhs_per_gpu": m, "rhs_total": m * world, "alpha": 1.0, "inputs": "scaled recipe (SURVEY 8(d)), seed 1235/777+rank",
                            "l2": "inputs (A 2 GiB + B 2 GiB per GPU) larger than L2; B restored from a pristine copy between steps outside the timed events",
                            "parallelism": f"rhs-sharded x{world}, A broadcast by NCCL inside every step" if world > 1 else "single GPU",
-                           "streams": args.streams, "leaf": h.get_option("leaf")},
+                           "streams": args.streams or "auto", "leaf": h.get_option("leaf"), "macro": h.get_option("macro")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "backward_error": berr, "tolerance": 1e-13, "wall_ms_per_step_incl_restore": t_wall / args.steps * 1e3,
                 "pct_of_fp64_peak": 100.0 * value / world / FP64_PEAK_TFLOPS}

@@ -70,7 +70,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
 /* Tunables (the reference hard-codes its thresholds, src/rectrxm.jl:52,63).  Keys:
  *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
- *   "streams"     number of RHS slabs run on concurrent streams (default 1)
+ *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 2048, 0 = off)
+ *   "streams"     number of RHS slabs run on concurrent streams (0 = automatic: one per 4096 vectors, at most 4)
  *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
 int64_t nla_get_option(nla_handle_t handle, const char *key);

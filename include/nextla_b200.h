@@ -77,6 +77,9 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "tc_bn"       N tile of the Float32/Float16 tcgen05 GEMM: 0 = automatic (256, or 128 when the 256-wide grid would not fill the SMs), 128, 256
  *   "tf32_raw_hi" Float32 3xTF32 split: 1 (default) = the raw FP32 tile is the hi operand (the tensor core drops the low 13 bits), 0 = mask explicitly
  *   "tc_chunk_k"  Float32: K extent accumulated in tensor memory before it is added into C with round-to-nearest (default 512; 0 = never)
+ *   "trmm_batched" Float32/Float16 multiply: 1 (default) = out-of-place batched schedule (one copy of B in the handle's workspace, all diagonal
+ *                 blocks in one launch, one triangular GEMM), 0 = the reference's in-place recursion
+ *   "pdl"         1 (default) = launch the tcgen05 kernels with programmatic dependent launch (prologue overlaps the predecessor's tail)
  *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
 int64_t nla_get_option(nla_handle_t handle, const char *key);

@@ -77,6 +77,7 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (int spin = 0; spin < 4096; spin++)
     if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();

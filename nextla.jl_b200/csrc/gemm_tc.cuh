@@ -29,8 +29,9 @@
 //  * Float16 stages are 48 KB (2 stages, 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop);
 //    Float32 stages are 96 KB (raw/hi + lo copies, 2 stages, 1 CTA per SM).  A 128 x 128 tile variant (3 stages) fills the
 //    machine when the 256-wide grid would not.
-//  * Epilogue: the old C tile is prefetched into L2 at kernel start; 32 columns (tcgen05.ld.32x32b.x32) per iteration
-//    with 32 independent loads in flight per thread; a warp's access to one column is one contiguous 64/128-byte segment.
+//  * Epilogue: the old C tile is prefetched into L2 at kernel start; 32 columns (tcgen05.ld.32x32b.x32) per iteration go
+//    through a per-warp FP32 staging tile in shared memory so that C is read and written with 16-byte accesses (element-wise
+//    2-byte stores straight from the TMEM row layout cost 9 us per 128 x 128 tile, measured with in-kernel timestamps).
 #pragma once
 #include "common.cuh"
 #include "gemm_f64.cuh"  // MAJ_MN / MAJ_K
@@ -62,7 +63,7 @@ template <typename T, int BN> struct TcShape {
   static constexpr int HALF_STAGE = A_BYTES + B_BYTES;     // raw (= hi) tiles; the lo copies follow for Float32
   static constexpr int STAGE = HALF_STAGE * (TcCfg<T>::PASSES == 3 ? 2 : 1);
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int SMEM = STAGES * STAGE + 1024;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + (TcCfg<T>::PASSES == 3 ? 16384 : 0);   // + drain staging for Float32
 };
 
 struct GemmTcParams {
@@ -75,6 +76,11 @@ struct GemmTcParams {
   int overwrite;      // 1: C <- post * sgn * A*B, the old contents of C are not read
   int raw_hi;         // Float32: 1 = leave the raw FP32 tile in place as the "hi" operand.  kind::tf32 ignores the 13 low mantissa bits
                       // (measured on B200: results bit-identical to explicit masking), so only the lo tile has to be written.
+  // K window per tile (batched TRMM, see nla_api.cu): t = tile index along M (or along N when win_on_n; N tile must be 128)
+  //   win_mode 0: k in [0, K)                          1: diagonal block, k in [128t, 128t+128) of the V operand, [0,128) of the other
+  //            2: k in [0, 128t)  (strictly below)     3: k in [128(t+1), K)  (strictly above)
+  int win_mode, win_on_n, win_shift_a;
+  unsigned long long* dbg;   // optional: 8 globaltimer stamps per CTA (probe builds; nullptr in production)
   int chunk_k;        // Float32: K extent accumulated in TMEM before it is promoted into C (0 = everything in one chunk)
   int tiles_m, tiles_n;
 };
@@ -123,8 +129,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int first_m = grp * TC_GROUP_M;
   const int gsz = min(TC_GROUP_M, p.tiles_m - first_m);
   const int rem = blockIdx.x - grp * per_group;
-  const int tm = first_m + rem % gsz;
-  const int tn = rem / gsz;
+  int tm = first_m + rem % gsz;
+  int tn = rem / gsz;
+
+  // K window of this tile
+  int kbeg = 0, klen = p.K, ash = 0, bsh = 0;
+  if (p.win_mode) {
+    if (p.win_mode == 2) {   // work grows with the tile index: start the heaviest tiles first
+      if (p.win_on_n) tn = p.tiles_n - 1 - tn; else tm = p.tiles_m - 1 - tm;
+    }
+    const int t = p.win_on_n ? tn : tm;
+    if (p.win_mode == 1) {
+      klen = min(128, p.K - 128 * t);
+      if (p.win_shift_a) ash = 128 * t; else bsh = 128 * t;
+    } else if (p.win_mode == 2) {
+      klen = min(p.K, 128 * t);
+    } else {
+      kbeg = 128 * (t + 1);
+      klen = p.K - kbeg;
+    }
+    if (klen <= 0) return;   // uniform for the CTA; nothing allocated yet
+  }
+
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue (barrier init, TMEM allocation,
+  // descriptor prefetch) while this one is still running; it blocks in griddepcontrol.wait until this grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#define NLA_STAMP(slot) do { if (p.dbg) p.dbg[blockIdx.x * 8 + (slot)] = global_timer_ns(); } while (0)
+  if (threadIdx.x == 0) NLA_STAMP(0);   // kernel entry
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -140,11 +171,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), TMEM_COLS);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched no global data; from here on the previous kernel's results are needed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) NLA_STAMP(1);   // prologue done (barriers, TMEM, dependency wait)
   const uint32_t tmem = tmem_slot;
-  const int nk = (p.K + BK - 1) / BK;
+  const int nk = (klen + BK - 1) / BK;
   // K is accumulated in TMEM in chunks; each finished chunk is added to C in registers with round-to-nearest by the drain
   // warps while the next chunk runs into the other TMEM tile.  The tensor core's own accumulation truncates, which biases
   // long same-sign sums (measured ~2^-24 relative per MMA); chunking bounds that for Float32.  Float16 uses one chunk.
@@ -154,8 +189,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      tma_prefetch_desc(&mapA);
-      tma_prefetch_desc(&mapB);
       const int am = p.a_mn0 + tm * TC_BM, bn = p.b_mn0 + tn * BN;
       for (int kt = 0; kt < nk; kt++) {
         const int s = kt % S, it = kt / S;
@@ -163,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, HALF_STAGE);
         const uint32_t sa = smem_base + s * STAGE, sb = sa + A_BYTES;
-        const int ak = p.a_k0 + kt * BK, bk = p.b_k0 + kt * BK;
+        const int ak = p.a_k0 + ash + kbeg + kt * BK, bk = p.b_k0 + bsh + kbeg + kt * BK;
         if (AMAJ == MAJ_K) {
           tma_load_2d(sa, &mapA, fb, ak, am);                                            // box {BK, 128}
         } else {
@@ -192,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       constexpr uint32_t A_SBO = A32 ? 512u : 1024u, B_SBO = B32 ? 512u : 1024u;
       constexpr uint32_t A_LAY = A32 ? UMMA_SW128_BASE32B : UMMA_SW128, B_LAY = B32 ? UMMA_SW128_BASE32B : UMMA_SW128;
       int kt = 0;
+      bool stamped = false;
       for (int c = 0; c < nchunks; c++) {
         const int buf = c % NBUF, use = c / NBUF;
         if (use > 0) {   // the drain warps must have emptied this TMEM tile (chunk c - NBUF)
@@ -205,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int s = kt % S, it = kt / S;
           mbar_wait_wd(smem_u32(F32 ? &conv_bar[s] : &full_bar[s]), it & 1);
           tc_fence_after();
+          if (!stamped) { NLA_STAMP(2); stamped = true; }   // first operand stage has landed
           const uint32_t sa = smem_base + s * STAGE, sb = sa + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / UK; kk++) {
@@ -225,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         tc_commit(smem_u32(&dfull_bar[buf]));
       }
+      NLA_STAMP(3);   // all MMAs issued
     }
     __syncwarp();
   } else if (warp < DRAIN_WARP0) {
@@ -254,8 +290,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int quarter = warp & 3;
     const int row = tm * TC_BM + quarter * 32 + lane;
     const bool row_ok = row < p.M;
-    T* crow = reinterpret_cast<T*>(p.C) + row;
+    T* cbase = reinterpret_cast<T*>(p.C);
+    T* crow = cbase + row;
     const int ncols = min(BN, p.N - tn * BN);   // valid columns of this tile
+    // per-warp FP32 staging tile (32 columns x 32 rows).  Float16: the operand ring is idle once the single accumulator chunk is
+    // complete, so its first 16 KB are reused; Float32 drains while the ring is live and has a dedicated region behind it.
+    float* stg = reinterpret_cast<float*>(smem_gen + (F32 ? S * STAGE : 0)) + (warp - DRAIN_WARP0) * 1024;
     if (!p.overwrite) {
       // pull the old C tile into L2 while the main loop runs: each warp touches its own 32 rows of every column
       if (row_ok && (lane % (32 / ES)) == 0)   // one lane per 32-byte sector
@@ -267,6 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait_wd(smem_u32(&dfull_bar[buf]), use & 1);
       tc_fence_after();
       const bool first = (c == 0), last = (c == nchunks - 1);
+      if (last && threadIdx.x == DRAIN_WARP0 * 32) NLA_STAMP(4);   // last accumulator chunk complete
       const bool need_old = !(first && p.overwrite);
       // rounding points of the reference: B .= alpha .* B rounds to T (src/rectrxm.jl:64) -> beta on the first chunk; the update
       // rounds once per chunk (src/matmul.jl:64 rounds once per update); the trailing scale (src/rectrxm.jl:72) -> post on the last
@@ -275,25 +316,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (c0 >= ncols) break;   // warp-uniform
-        const int colbase = tn * BN + c0;
+        // TMEM -> registers (this thread: one row, 32 columns) -> per-warp FP32 staging tile [column][row] in shared memory
         uint32_t r[32];
         tmem_ld32(dt + (uint32_t)c0, r);
-        float old[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          old[j] = 0.f;
-          if (need_old && row_ok && c0 + j < ncols) old[j] = tc_to_float<T>(crow[(long long)(colbase + j) * p.ldc]);
-        }
         tmem_ld_wait();
+        __syncwarp();   // the previous pass has finished reading the staging tile
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          if (row_ok && c0 + j < ncols) {
-            const float a = __uint_as_float(r[j]);
-            float v = old[j];
-            if (beta != 1.0f) v = tc_to_float<T>(tc_from_float<T>(beta * v));
-            v += p.sgn * a;
-            if (post != 1.0f) v = post * tc_to_float<T>(tc_from_float<T>(v));
-            crow[(long long)(colbase + j) * p.ldc] = tc_from_float<T>(v);
+        for (int j = 0; j < 32; j++) stg[j * 32 + lane] = __uint_as_float(r[j]);
+        __syncwarp();
+        // shared memory -> C with 16-byte accesses: a lane owns VEC consecutive rows of one column, the warp covers CPP columns per pass
+        constexpr int VEC = 16 / ES, LPC = 32 / VEC, CPP = 32 / LPC, PASSES = 32 / CPP;
+        const int rseg = (lane % LPC) * VEC;
+        const int grow = tm * TC_BM + quarter * 32 + rseg;
+        uint4 oldv[PASSES];
+        if (need_old) {
+#pragma unroll
+          for (int ps = 0; ps < PASSES; ps++) {
+            const int col = c0 + ps * CPP + lane / LPC;
+            oldv[ps] = make_uint4(0u, 0u, 0u, 0u);
+            if (col < ncols && grow + VEC <= p.M) {
+              oldv[ps] = *reinterpret_cast<const uint4*>(cbase + grow + (long long)(tn * BN + col) * p.ldc);
+            } else if (col < ncols && grow < p.M) {   // ragged last rows: element-wise
+              T tmp[VEC];
+#pragma unroll
+              for (int e = 0; e < VEC; e++) tmp[e] = (grow + e < p.M) ? cbase[grow + e + (long long)(tn * BN + col) * p.ldc] : tc_from_float<T>(0.f);
+              oldv[ps] = *reinterpret_cast<const uint4*>(tmp);
+            }
+          }
+        }
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ps++) {
+          const int cl = ps * CPP + lane / LPC, col = c0 + cl;
+          if (col < ncols && grow < p.M) {
+            T outv[VEC];
+            const T* ov = reinterpret_cast<const T*>(&oldv[ps]);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+              float v = need_old ? tc_to_float<T>(ov[e]) : 0.f;
+              if (beta != 1.0f) v = tc_to_float<T>(tc_from_float<T>(beta * v));
+              v += p.sgn * stg[cl * 32 + rseg + e];
+              if (post != 1.0f) v = post * tc_to_float<T>(tc_from_float<T>(v));
+              outv[e] = tc_from_float<T>(v);
+            }
+            T* dst = cbase + grow + (long long)(tn * BN + col) * p.ldc;
+            if (grow + VEC <= p.M) {
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outv);
+            } else {
+#pragma unroll
+              for (int e = 0; e < VEC; e++) if (grow + e < p.M) dst[e] = outv[e];
+            }
           }
         }
       }
@@ -305,9 +376,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   // ===== teardown =====
+  if (threadIdx.x == DRAIN_WARP0 * 32) NLA_STAMP(5);   // drain done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
+  if (threadIdx.x == 32) NLA_STAMP(6);   // TMEM released
+#undef NLA_STAMP
 }
 
 }  // namespace nla

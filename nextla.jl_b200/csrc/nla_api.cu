@@ -46,6 +46,10 @@ struct nla_context {
   cudaEvent_t fork_event;
   // K-major copies of the prepared diagonal blocks (inverse / masked triangle) for the Float32/Float16 tensor-core leaves
   void* diag_ws; size_t diag_ws_bytes;
+  void* bcopy_ws; size_t bcopy_ws_bytes;   // pristine copy of B for the batched (out-of-place) TRMM
+  int64_t trmm_batched;
+  int64_t pdl;
+  int64_t tc_dbg;       // device pointer to per-CTA timing stamps (probes only)
   // device staging for the host-buffer entry point
   void* stage_a; size_t stage_a_bytes;
   void* stage_b; size_t stage_b_bytes;
@@ -262,9 +266,15 @@ static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const
     NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<T, AMAJ, BMAJ, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<T, BN>::SMEM));
     configured[ctx->device & 63] = true;
   }
-  gemm_tc_kernel<T, AMAJ, BMAJ, BN><<<gp.tiles_m * gp.tiles_n, TcCfg<T>::THREADS, TcShape<T, BN>::SMEM, st>>>(mA, mB, gp);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(gp.tiles_m * gp.tiles_n)); cfg.blockDim = dim3(TcCfg<T>::THREADS);
+  cfg.dynamicSmemBytes = TcShape<T, BN>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap this kernel's prologue with its predecessor's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx->pdl ? 1 : 0;
+  NLA_CUDA(ctx, cudaLaunchKernelEx(&cfg, gemm_tc_kernel<T, AMAJ, BMAJ, BN>, mA, mB, gp));
   ctx->launches++;
-  NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
 }
 
@@ -278,10 +288,11 @@ static int tc_pick_bn(nla_context* ctx, int64_t M, int64_t N) {
 // mB256 / mB128: the B operand's tensor map for either N tile (identical for MN-major operands)
 template <typename T>
 static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMap& mA, const CUtensorMap& mB256, const CUtensorMap& mB128,
-                          GemmTcParams gp, cudaStream_t st) {
-  const int bn = tc_pick_bn(ctx, gp.M, gp.N);
+                          GemmTcParams gp, cudaStream_t st, int force_bn = 0) {
+  const int bn = force_bn ? force_bn : tc_pick_bn(ctx, gp.M, gp.N);
   gp.raw_hi = (int)ctx->tf32_raw_hi;
   gp.chunk_k = (int)ctx->tc_chunk_k;
+  gp.dbg = (unsigned long long*)ctx->tc_dbg;
   gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + bn - 1) / bn;
   if (bn == 256) {
     if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K, 256>(ctx, mA, mB256, gp, st);
@@ -487,6 +498,7 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
       if (ctx->diag_ws_bytes < need) {
         if (ctx->diag_ws) cudaFree(ctx->diag_ws);
         ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
+  ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
         NLA_CUDA(ctx, cudaMalloc(&ctx->diag_ws, need));
         ctx->diag_ws_bytes = need;
       }
@@ -536,6 +548,79 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
   return NLA_OK;
 }
 
+// Batched TRMM for the tensor-core path (Float32 / Float16).  A multiply has no dependency chain: every block row of
+// Y = tri(Teff) * B needs only ORIGINAL rows of B.  The reference's recursion (src/rectrxm.jl:159-197) serialises them only
+// because it works in place; with one pristine copy of B the whole product is three launches that fill the machine:
+//   (1) B0 <- B (device copy into the handle's workspace)
+//   (2) every diagonal block at once:  V[i] <- alpha * tri(Teff[i,i]) * V[i]           (in place, one tile per block)
+//   (3) one triangular GEMM:           V[i] += alpha * sum_{j<i or j>i} Teff[i,j] * B0[j]   (per-tile K window)
+// instead of 2n/128 - 1 dependent launches.  Same arithmetic per entry up to the order of the block sums.
+template <typename T>
+static int trmm_batched_tc(nla_context* ctx, const Problem& P, const TmaMaps& maps, cudaStream_t st) {
+  const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
+  const int64_t ldc = (brows + 15) & ~15ll;   // compact pitch, 16-byte aligned for any element size
+  const size_t need = (size_t)ldc * bcols * sizeof(T);
+  if (ctx->bcopy_ws_bytes < need) {
+    if (ctx->bcopy_ws) cudaFree(ctx->bcopy_ws);
+    ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0;
+    NLA_CUDA(ctx, cudaMalloc(&ctx->bcopy_ws, need));
+    ctx->bcopy_ws_bytes = need;
+  }
+  CUtensorMap mapC, mapC128;
+  if (!encode_map_tc<T>(ctx, &mapC, ctx->bcopy_ws, brows, bcols, ldc, maps.majV, P.right) ||
+      !encode_map_tc<T>(ctx, &mapC128, ctx->bcopy_ws, brows, bcols, ldc, maps.majV, P.right, 128))
+    return NLA_ERR_UNSUPPORTED;
+  NLA_CUDA(ctx, cudaMemcpy2DAsync(ctx->bcopy_ws, (size_t)ldc * sizeof(T), P.B, (size_t)P.ldb * sizeof(T), (size_t)brows * sizeof(T), (size_t)bcols,
+                                  cudaMemcpyDeviceToDevice, st));
+  nla_context::ProfRec pr{};
+  auto prof_begin = [&](int kind, double flops) -> int {
+    if (!ctx->profile) return NLA_OK;
+    for (cudaEvent_t* e : {&pr.e0, &pr.e1}) {
+      if (ctx->prof_pool.empty()) { NLA_CUDA(ctx, cudaEventCreate(e)); } else { *e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    }
+    pr.kind = kind; pr.flops = flops;
+    NLA_CUDA(ctx, cudaEventRecord(pr.e0, st));
+    return NLA_OK;
+  };
+  auto prof_end = [&]() -> int {
+    if (!ctx->profile) return NLA_OK;
+    NLA_CUDA(ctx, cudaEventRecord(pr.e1, st));
+    ctx->prof.push_back(pr);
+    return NLA_OK;
+  };
+  const double dn = (double)P.n, dm = (double)P.m;
+  // (2) all diagonal blocks
+  GemmTcParams lp{};
+  lp.beta = 0.f; lp.sgn = 1.f; lp.post = (float)P.alpha; lp.overwrite = 1; lp.ldc = P.ldb; lp.C = P.B;
+  lp.K = (int)P.n; lp.win_mode = 1;
+  int rc = prof_begin(0, 128.0 * dn * dm);
+  if (rc != NLA_OK) return rc;
+  if (!P.right) {
+    lp.M = (int)P.n; lp.N = (int)P.m; lp.win_on_n = 0; lp.win_shift_a = 0;   // A operand = W (block-local k), B operand = V (k shifted to the block)
+    rc = launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, maps.mapV, maps.mapV128, lp, st);
+  } else {
+    lp.M = (int)P.m; lp.N = (int)P.n; lp.win_on_n = 1; lp.win_shift_a = 1;   // A operand = V (k shifted), B operand = W
+    rc = launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, maps.mapV, maps.mapW, maps.mapW128, lp, st, 128);
+  }
+  if (rc != NLA_OK) return rc;
+  if ((rc = prof_end()) != NLA_OK) return rc;
+  if (P.n <= DP_B) return NLA_OK;
+  // (3) the strictly triangular part against the pristine copy
+  GemmTcParams gp{};
+  gp.beta = 1.f; gp.sgn = (float)P.alpha; gp.post = 1.f; gp.overwrite = 0; gp.ldc = P.ldb; gp.C = P.B;
+  gp.K = (int)P.n; gp.win_mode = P.lower ? 2 : 3;
+  if ((rc = prof_begin(1, (dn * dn - 128.0 * dn) * dm)) != NLA_OK) return rc;
+  if (!P.right) {
+    gp.M = (int)P.n; gp.N = (int)P.m; gp.win_on_n = 0;
+    rc = launch_gemm_tc<T>(ctx, maps.majT, MAJ_K, maps.mapT, mapC, mapC128, gp, st);
+  } else {
+    gp.M = (int)P.m; gp.N = (int)P.n; gp.win_on_n = 1;
+    rc = launch_gemm_tc<T>(ctx, MAJ_MN, maps.majT, mapC, maps.mapT, maps.mapT128, gp, st, 128);
+  }
+  if (rc != NLA_OK) return rc;
+  return prof_end();
+}
+
 static int ensure_streams(nla_context* ctx, int64_t S) {
   while ((int64_t)ctx->streams.size() < S) {
     cudaStream_t s; cudaEvent_t e;
@@ -558,6 +643,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
       const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
       int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream);
       if (rc != NLA_OK) return rc;
+      if (!P.solve && ctx->trmm_batched) return trmm_batched_tc<T>(ctx, P, maps, stream);
     }
   }
 
@@ -674,6 +760,7 @@ int nla_destroy(nla_handle_t h) {
   if (h->stage_a) cudaFree(h->stage_a);
   if (h->stage_b) cudaFree(h->stage_b);
   if (h->diag_ws) cudaFree(h->diag_ws);
+  if (h->bcopy_ws) cudaFree(h->bcopy_ws);
   h->magic = 0;
   delete h;
   return NLA_OK;
@@ -690,6 +777,9 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
   if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
+  if (!strcmp(key, "trmm_batched")) { h->trmm_batched = value != 0; return NLA_OK; }
+  if (!strcmp(key, "pdl")) { h->pdl = value != 0; return NLA_OK; }
+  if (!strcmp(key, "tc_dbg")) { h->tc_dbg = value; return NLA_OK; }
   if (!strcmp(key, "tc_chunk_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_chunk_k = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
   return NLA_ERR_UNSUPPORTED;
@@ -705,6 +795,8 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
   if (!strcmp(key, "tf32_raw_hi")) return h->tf32_raw_hi;
   if (!strcmp(key, "tc_chunk_k")) return h->tc_chunk_k;
+  if (!strcmp(key, "trmm_batched")) return h->trmm_batched;
+  if (!strcmp(key, "pdl")) return h->pdl;
   return -1;
 }
 
@@ -800,7 +892,7 @@ static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int6
   if constexpr (!std::is_same<T, double>::value) {
     // tcgen05 path: operands straight from the caller's matrices when they satisfy the TMA constraints
     const int64_t ar = at ? K : M, ac = at ? M : K, br = bt ? N : K, bc = bt ? K : N;
-    if (!ctx->force_simt && !(at && bt) && tc_ok<T>(A, ar, ac, lda) && tc_ok<T>(B, br, bc, ldb)) {
+    if (!ctx->force_simt && !(at && bt) && tc_ok<T>(A, ar, ac, lda) && tc_ok<T>(B, br, bc, ldb) && tc_ok<T>(C, M, N, ldc)) {
       const int majA = at ? MAJ_K : MAJ_MN, majB = bt ? MAJ_MN : MAJ_K;
       CUtensorMap mA, mB, mB128;
       if (encode_map_tc<T>(ctx, &mA, A, ar, ac, lda, majA, true) && encode_map_tc<T>(ctx, &mB, B, br, bc, ldb, majB, false) &&

@@ -345,6 +345,13 @@ def test_tensor_core_path_matches_simt_path(nla, gpu, dtype):
             gpu.set_option("force_simt", 0)
         assert rel(got, ref) < (5e-6 if dtype == np.float32 else 5e-3), (side, uplo, trans, func)
         assert rp.error_metric(side, uplo, trans, -0.5, func, A, B0, got) < TOL[dtype]
+        if func == "M":   # the in-place recursion (reference order) against the default batched out-of-place schedule
+            gpu.set_option("trmm_batched", 0)
+            try:
+                rec = run_gpu(nla, side, uplo, trans, -0.5, func, A, B0)
+            finally:
+                gpu.set_option("trmm_batched", 1)
+            assert rel(got, rec) < (5e-6 if dtype == np.float32 else 5e-3), (side, uplo, trans, func)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float16])

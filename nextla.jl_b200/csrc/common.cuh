@@ -135,9 +135,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // Shared-memory matrix descriptor of tcgen05.mma (descriptor version 1 = sm_100):
 //   bits [0,14) start address >> 4, [16,30) leading-dimension byte offset >> 4, [32,46) stride-dimension byte offset >> 4,
-//   [46,48) version, [61,64) swizzle mode: 2 = SWIZZLE_128B (16-byte chunks XOR row), 1 = SWIZZLE_128B with 32-byte
+//   [46,48) version, [61,64) swizzle mode: 2 = SWIZZLE_128B (16-byte chunks XOR row), 4 = SWIZZLE_64B, 1 = SWIZZLE_128B with 32-byte
 //   chunks ("128B_BASE32B": the only layout tcgen05 accepts for MN-major 32-bit operands).
-constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_BASE32B = 1;
+constexpr uint32_t UMMA_SW128 = 2, UMMA_SW128_BASE32B = 1, UMMA_SW64 = 4;
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) |
          (1ull << 46) | ((uint64_t)layout << 61);

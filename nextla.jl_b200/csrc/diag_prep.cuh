@@ -10,9 +10,10 @@
 // P_i(r, k) -- so that it is the A operand of the left-side leaf and the B operand of the right-side leaf (gemm_tc.cuh).
 // Rows/columns beyond a ragged last block are zero.
 //
-// One CTA (128 threads) per block.  Upper blocks are reversed to lower ones on load and reversed back on store.  Thread j
-// owns column j of the inverse: forward substitution in FP64 with the triangular block (exact in FP32) and the growing
-// inverse in shared memory; all threads read the same L(r,k) (broadcast) and their own column (conflict free).
+// One CTA (1024 threads) per block.  Upper blocks are reversed to lower ones on load and reversed back on store.  Eight
+// lanes share column j of the inverse: forward substitution in FP64 with the triangular block (exact in FP32) and the growing
+// inverse in shared memory; the dot product of every row is split eight ways and reduced with warp shuffles, which cuts the
+// serial chain from ~8000 dependent FMAs (one thread per column: 250 us measured) to ~1000.
 #pragma once
 #include "common.cuh"
 
@@ -20,6 +21,7 @@ namespace nla {
 
 constexpr int DP_B = 128;                       // diagonal block order == GEMM M tile == recursion cutoff of the TC path
 constexpr int DP_LP = DP_B + 1;
+constexpr int DP_THREADS = 1024, DP_SPLIT = DP_THREADS / DP_B;   // lanes per column
 constexpr int DP_SMEM_BYTES = DP_B * DP_LP * 4 + DP_B * DP_LP * 8;
 
 template <typename T>
@@ -32,7 +34,7 @@ struct DiagPrepParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(DP_B) diag_prep_kernel(const DiagPrepParams<T> p) {
+__global__ void __launch_bounds__(DP_THREADS) diag_prep_kernel(const DiagPrepParams<T> p) {
   extern __shared__ __align__(16) uint8_t dp_smem[];
   float* Ls = reinterpret_cast<float*>(dp_smem);                       // [r][k], pitch DP_LP (normalised to lower)
   double* Xs = reinterpret_cast<double*>(dp_smem + DP_B * DP_LP * 4);  // [r][j], pitch DP_LP
@@ -44,8 +46,9 @@ __global__ void __launch_bounds__(DP_B) diag_prep_kernel(const DiagPrepParams<T>
 
   // ---- load the block, masked to its triangle, normalised to lower by index reversal ----
   const bool r_contig = (p.t_rs == 1);
-  for (int o = 0; o < DP_B; o++) {
-    const int r = r_contig ? tid : o, k = r_contig ? o : tid;   // thread index along the contiguous direction of A
+  for (int e = tid; e < DP_B * DP_B; e += DP_THREADS) {
+    const int fast = e % DP_B, slow = e / DP_B;                   // `fast` runs along the contiguous direction of A
+    const int r = r_contig ? fast : slow, k = r_contig ? slow : fast;
     float v = 0.f;
     if (r < t && k < t) {
       const int R = p.lower ? r : t - 1 - r, K = p.lower ? k : t - 1 - k;
@@ -58,31 +61,29 @@ __global__ void __launch_bounds__(DP_B) diag_prep_kernel(const DiagPrepParams<T>
   __syncthreads();
 
   if (p.solve) {
-    // ---- column `tid` of inv(L): x_r = (delta_{r,tid} - sum_{k=tid}^{r-1} L(r,k) x_k) / L(r,r) ----
-    const int j = tid;
-    for (int r = 0; r < j; r++) Xs[r * DP_LP + j] = 0.0;
-    for (int r = j; r < DP_B; r++) {
-      double s0 = (r == j) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    // ---- column j of inv(L): x_r = (delta_{r,j} - sum_{k=j}^{r-1} L(r,k) x_k) / L(r,r); lanes part = 0..7 split the sum ----
+    const int j = tid / DP_SPLIT, part = tid % DP_SPLIT;
+    for (int r = part; r < j; r += DP_SPLIT) Xs[r * DP_LP + j] = 0.0;
+    const int j0 = (tid / 32) * (32 / DP_SPLIT);   // first column of this warp: every lane runs the same trip count (full-mask shuffles)
+    for (int r = j0; r < DP_B; r++) {
       const float* Lr = Ls + r * DP_LP;
-      int k = j;
-      for (; k + 3 < r; k += 4) {
-        s0 -= (double)Lr[k] * Xs[k * DP_LP + j];
-        s1 -= (double)Lr[k + 1] * Xs[(k + 1) * DP_LP + j];
-        s2 -= (double)Lr[k + 2] * Xs[(k + 2) * DP_LP + j];
-        s3 -= (double)Lr[k + 3] * Xs[(k + 3) * DP_LP + j];
-      }
-      for (; k < r; k++) s0 -= (double)Lr[k] * Xs[k * DP_LP + j];
-      Xs[r * DP_LP + j] = ((s0 + s1) + (s2 + s3)) / (double)Lr[r];
+      double s = 0.0;
+      for (int k = j + part; k < r; k += DP_SPLIT) s -= (double)Lr[k] * Xs[k * DP_LP + j];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (part == 0 && r >= j) Xs[r * DP_LP + j] = (s + ((r == j) ? 1.0 : 0.0)) / (double)Lr[r];
+      __syncwarp();
     }
   } else {
-    for (int r = 0; r < DP_B; r++) Xs[r * DP_LP + tid] = (double)Ls[r * DP_LP + tid];
+    for (int e = tid; e < DP_B * DP_B; e += DP_THREADS) Xs[(e / DP_B) * DP_LP + e % DP_B] = (double)Ls[(e / DP_B) * DP_LP + e % DP_B];
   }
   __syncthreads();
 
   // ---- store K-major (k contiguous), reversing back for upper blocks ----
   T* Wb = p.W + (long long)off * DP_B;
-  for (int r = 0; r < DP_B; r++) {
-    const int k = tid;
+  for (int e = tid; e < DP_B * DP_B; e += DP_THREADS) {
+    const int k = e % DP_B, r = e / DP_B;
     float v = 0.f;
     if (r < t && k < t) {
       const int rr = p.lower ? r : t - 1 - r, kk = p.lower ? k : t - 1 - k;   // position in the normalised (lower) block

@@ -49,7 +49,7 @@ template <> struct TcCfg<__half> {
   static constexpr uint32_t FMT = 0;  // F16
 };
 template <> struct TcCfg<float> {
-  static constexpr int BK = 32, UK = 8, PASSES = 3, MIN_CTAS = 1;
+  static constexpr int BK = 16, UK = 8, PASSES = 3, MIN_CTAS = 1;   // 64-byte K rows: half-size stages, twice the pipeline depth
   static constexpr int THREADS = 320;   // TMA warp, MMA warp, 4 hi/lo splitter warps, 4 drain warps
   static constexpr int NBUF = 2, CHUNK_K = 512;   // two accumulator tiles; every 512 of K is promoted into C with round-to-nearest
   static constexpr uint32_t FMT = 2;  // TF32
@@ -58,11 +58,11 @@ template <> struct TcCfg<float> {
 // Tile shapes: BN = 256 is the throughput shape (one MMA reads 12 KB of shared memory per 128 cycles); BN = 128 is used when
 // the 256-wide grid would leave SMs idle (small diagonal blocks, few right-hand sides).
 template <typename T, int BN> struct TcShape {
-  static constexpr int A_BYTES = TC_BM * 128;              // BM rows x 128 B of K (or BK rows x BM elements)
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_BYTES = TC_BM * TcCfg<T>::BK * (int)sizeof(T);   // BM rows x BK elements of K (either majorness)
+  static constexpr int B_BYTES = BN * TcCfg<T>::BK * (int)sizeof(T);
   static constexpr int HALF_STAGE = A_BYTES + B_BYTES;     // raw (= hi) tiles; the lo copies follow for Float32
   static constexpr int STAGE = HALF_STAGE * (TcCfg<T>::PASSES == 3 ? 2 : 1);
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int STAGES = (sizeof(T) == 4 ? 2 : 1) * ((BN == 256) ? 2 : 3);   // Float16: 2 x 48 KB / 3 x 32 KB; Float32: 4 x 48 KB / 6 x 32 KB
   static constexpr int SMEM = STAGES * STAGE + 1024 + (TcCfg<T>::PASSES == 3 ? 16384 : 0);   // + drain staging for Float32
 };
 
@@ -222,8 +222,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // MN-major 32-bit operands: tcgen05 only accepts the 128-byte swizzle with 32-byte chunks, whose atom is 4 k-rows
       // (512 B) instead of 8 (the TMA map of such an operand uses CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B to match).
       constexpr bool A32 = (AMAJ == MAJ_MN) && ES == 4, B32 = (BMAJ == MAJ_MN) && ES == 4;
-      constexpr uint32_t A_SBO = A32 ? 512u : 1024u, B_SBO = B32 ? 512u : 1024u;
-      constexpr uint32_t A_LAY = A32 ? UMMA_SW128_BASE32B : UMMA_SW128, B_LAY = B32 ? UMMA_SW128_BASE32B : UMMA_SW128;
+      // K-major operands: rows of BK*ES bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups 8 rows apart.
+      constexpr uint32_t KROW = (uint32_t)(BK * ES);
+      constexpr uint32_t K_LAY = (KROW == 128) ? UMMA_SW128 : UMMA_SW64;
+      constexpr uint32_t A_SBO = (AMAJ == MAJ_K) ? 8u * KROW : (A32 ? 512u : 1024u), B_SBO = (BMAJ == MAJ_K) ? 8u * KROW : (B32 ? 512u : 1024u);
+      constexpr uint32_t A_LAY = (AMAJ == MAJ_K) ? K_LAY : (A32 ? UMMA_SW128_BASE32B : UMMA_SW128);
+      constexpr uint32_t B_LAY = (BMAJ == MAJ_K) ? K_LAY : (B32 ? UMMA_SW128_BASE32B : UMMA_SW128);
+      static_assert(KROW == 128 || KROW == 64, "K-major rows must be 128 or 64 bytes");
       int kt = 0;
       bool stamped = false;
       for (int c = 0; c < nchunks; c++) {

@@ -240,13 +240,17 @@ static int tc_box_cols(int maj, bool a_role, int bn) { return maj == MAJ_K ? (a_
 template <typename T>
 static bool encode_map_tc(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj, bool a_role, int bn = 256) {
   const int box_cols = tc_box_cols<T>(maj, a_role, bn);
-  // MN-major 32-bit operands need the 32-byte-chunk swizzle (see gemm_tc.cuh)
-  const CUtensorMapSwizzle sw = (maj == MAJ_MN && sizeof(T) == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  // K-major operands: rows of BK elements (128 bytes for Float16, 64 bytes for Float32) with the matching swizzle;
+  // MN-major operands: 128 bytes of M/N per row; 32-bit ones need the 32-byte-chunk swizzle (see gemm_tc.cuh)
+  const int row_bytes = maj == MAJ_K ? TcCfg<T>::BK * (int)sizeof(T) : 128;
+  const CUtensorMapSwizzle sw = (maj == MAJ_MN && sizeof(T) == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : row_bytes == 64                  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                   : CU_TENSOR_MAP_SWIZZLE_128B;
   if (!ctx->encode) return false;
   const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(T)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(T)), (cuuint32_t)box_cols};
+  cuuint32_t box[2] = {(cuuint32_t)(row_bytes / sizeof(T)), (cuuint32_t)box_cols};
   cuuint32_t es[2] = {1, 1};
   CUresult r = ctx->encode(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -316,7 +320,7 @@ static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t 
   }
   DiagPrepParams<T> dp;
   dp.A = A; dp.t_rs = t_rs; dp.t_cs = t_cs; dp.n = (int)n; dp.lower = lower; dp.solve = solve; dp.block0 = (int)block0; dp.W = W;
-  diag_prep_kernel<T><<<(unsigned)nblocks, DP_B, DP_SMEM_BYTES, st>>>(dp);
+  diag_prep_kernel<T><<<(unsigned)nblocks, DP_THREADS, DP_SMEM_BYTES, st>>>(dp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
@@ -650,7 +654,8 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   // RHS vectors are independent: optionally run S slabs of vectors on concurrent streams so that the
   // small-K levels and the leaves of one slab overlap with the GEMMs of another.
   // default (option 0): one slab per 4096 vectors, at most 4 (measured on C2: 1 -> 131.9 ms, 4 -> 130.3 ms)
-  int64_t S = ctx->nstreams > 0 ? ctx->nstreams : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
+  // The tcgen05 kernels fill the machine from one stream (measured: FP16 n = m = 16384, 1 slab 6.0 ms, 4 slabs 7.0 ms).
+  int64_t S = ctx->nstreams > 0 ? ctx->nstreams : maps.tc ? 1 : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
   const int64_t gran = maps.tc ? 256 : 128;
   if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
   if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);

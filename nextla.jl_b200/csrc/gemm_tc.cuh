@@ -355,11 +355,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (col < ncols && grow < p.M) {
             T outv[VEC];
             const T* ov = reinterpret_cast<const T*>(&oldv[ps]);
+            float accv[VEC];   // 16-byte shared-memory reads: consecutive lanes read consecutive 16/32-byte pieces (no bank conflicts)
+#pragma unroll
+            for (int e = 0; e < VEC; e += 4) *reinterpret_cast<float4*>(&accv[e]) = *reinterpret_cast<const float4*>(&stg[cl * 32 + rseg + e]);
 #pragma unroll
             for (int e = 0; e < VEC; e++) {
               float v = need_old ? tc_to_float<T>(ov[e]) : 0.f;
               if (beta != 1.0f) v = tc_to_float<T>(tc_from_float<T>(beta * v));
-              v += p.sgn * stg[cl * 32 + rseg + e];
+              v += p.sgn * accv[e];
               if (post != 1.0f) v = post * tc_to_float<T>(tc_from_float<T>(v));
               outv[e] = tc_from_float<T>(v);
             }

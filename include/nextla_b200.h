@@ -75,6 +75,7 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 2048, 0 = off)
  *   "streams"     number of RHS slabs run on concurrent streams (0 = automatic: one per 4096 vectors, at most 4)
  *   "tc_bn"       N tile of the Float32/Float16 tcgen05 GEMM: 0 = automatic (256, or 128 when the 256-wide grid would not fill the SMs), 128, 256
+ *   "tc_cg"       CTA pairs (tcgen05 cta_group::2, 256 x 256 tile per pair) for the large updates: 0 = automatic, 1 = never, 2 = whenever M > 128
  *   "tf32_raw_hi" Float32 3xTF32 split: 1 (default) = the raw FP32 tile is the hi operand (the tensor core drops the low 13 bits), 0 = mask explicitly
  *   "tc_chunk_k"  Float32: K extent accumulated in tensor memory before it is added into C with round-to-nearest (default 512; 0 = never)
  *   "trmm_batched" Float32/Float16 multiply: 1 (default) = out-of-place batched schedule (one copy of B in the handle's workspace, all diagonal

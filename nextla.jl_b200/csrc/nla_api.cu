@@ -13,6 +13,7 @@
 #include "leaf.cuh"
 #include "slab_f64.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "diag_prep.cuh"
 
 using namespace nla;
@@ -33,6 +34,7 @@ struct nla_context {
   int64_t nstreams;
   int64_t profile;
   int64_t tc_bn;        // Float32/Float16 GEMM N tile: 0 = automatic, 128 or 256 = forced
+  int64_t tc_cg;        // CTA pairs (cta_group::2) for the large updates: 0 = automatic, 1 = never, 2 = whenever M > 128
   int64_t tf32_raw_hi;  // see GemmTcParams::raw_hi
   int64_t tc_chunk_k;   // see GemmTcParams::chunk_k
   int sm_count;
@@ -282,6 +284,27 @@ static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const
   return NLA_OK;
 }
 
+// CTA-pair variant (gemm_tc2.cuh): cluster of 2, M = 256 per tcgen05.mma
+template <typename T, int AMAJ, int BMAJ>
+static int launch_gemm_tc2_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB128, const GemmTcParams& gp, cudaStream_t st) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc2_kernel<T, AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<T>::SMEM));
+    configured[ctx->device & 63] = true;
+  }
+  const int pairs_m = (gp.tiles_m + 1) / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs_m * gp.tiles_n)); cfg.blockDim = dim3(TcCfg<T>::THREADS);
+  cfg.dynamicSmemBytes = Tc2Shape<T>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx->pdl ? 1 : 0;
+  NLA_CUDA(ctx, cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<T, AMAJ, BMAJ>, mA, mB128, gp));
+  ctx->launches++;
+  return NLA_OK;
+}
+
 // N tile of a launch: 256 unless that grid would leave SMs idle
 static int tc_pick_bn(nla_context* ctx, int64_t M, int64_t N) {
   if (ctx->tc_bn == 128 || ctx->tc_bn == 256) return (int)ctx->tc_bn;
@@ -289,14 +312,34 @@ static int tc_pick_bn(nla_context* ctx, int64_t M, int64_t N) {
   return (tiles256 < ctx->sm_count && N > 128) ? 128 : 256;
 }
 
+// CTA pairs for the launches that fill the machine with 128 x 256 tiles anyway (the large updates): 2/3 of the operand traffic per SM
+template <typename T>
+static bool tc_pick_pair(nla_context* ctx, const GemmTcParams& gp) {
+  if (gp.win_mode != 0 || ctx->tc_bn == 128) return false;
+  if (ctx->tc_cg == 1) return false;
+  if (ctx->tc_cg == 2) return gp.M > 128;
+  // measured on B200: Float16 top-level update 1255 -> 1413 TFLOP/s with pairs; Float32 (3xTF32 + splitter warps) 206 -> 140, so
+  // the automatic choice keeps Float32 on single CTAs
+  if (sizeof(T) == 4) return false;
+  const int64_t tiles256 = ((int64_t)(gp.M + TC_BM - 1) / TC_BM) * ((gp.N + 255) / 256);
+  return gp.M >= 256 && tiles256 >= ctx->sm_count;
+}
+
 // mB256 / mB128: the B operand's tensor map for either N tile (identical for MN-major operands)
 template <typename T>
 static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMap& mA, const CUtensorMap& mB256, const CUtensorMap& mB128,
                           GemmTcParams gp, cudaStream_t st, int force_bn = 0) {
-  const int bn = force_bn ? force_bn : tc_pick_bn(ctx, gp.M, gp.N);
   gp.raw_hi = (int)ctx->tf32_raw_hi;
   gp.chunk_k = (int)ctx->tc_chunk_k;
   gp.dbg = (unsigned long long*)ctx->tc_dbg;
+  if (!force_bn && tc_pick_pair<T>(ctx, gp)) {
+    gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + 255) / 256;
+    if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc2_variant<T, MAJ_MN, MAJ_K>(ctx, mA, mB128, gp, st);
+    if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc2_variant<T, MAJ_K, MAJ_K>(ctx, mA, mB128, gp, st);
+    if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc2_variant<T, MAJ_MN, MAJ_MN>(ctx, mA, mB128, gp, st);
+    return NLA_ERR_UNSUPPORTED;
+  }
+  const int bn = force_bn ? force_bn : tc_pick_bn(ctx, gp.M, gp.N);
   gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + bn - 1) / bn;
   if (bn == 256) {
     if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc_variant<T, MAJ_MN, MAJ_K, 256>(ctx, mA, mB256, gp, st);
@@ -736,7 +779,7 @@ int nla_create(nla_handle_t* handle, int device) {
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
   ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 2048;
-  ctx->tc_bn = 0; ctx->tf32_raw_hi = 1; ctx->tc_chunk_k = TcCfg<float>::CHUNK_K; ctx->sm_count = 148;
+  ctx->tc_bn = 0; ctx->tc_cg = 0; ctx->tf32_raw_hi = 1; ctx->tc_chunk_k = TcCfg<float>::CHUNK_K; ctx->sm_count = 148;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
@@ -781,6 +824,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
+  if (!strcmp(key, "tc_cg")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_cg = value; return NLA_OK; }
   if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
   if (!strcmp(key, "trmm_batched")) { h->trmm_batched = value != 0; return NLA_OK; }
   if (!strcmp(key, "pdl")) { h->pdl = value != 0; return NLA_OK; }
@@ -798,6 +842,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "profile")) return h->profile;
   if (!strcmp(key, "macro")) return h->macro;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
+  if (!strcmp(key, "tc_cg")) return h->tc_cg;
   if (!strcmp(key, "tf32_raw_hi")) return h->tf32_raw_hi;
   if (!strcmp(key, "tc_chunk_k")) return h->tc_chunk_k;
   if (!strcmp(key, "trmm_batched")) return h->trmm_batched;

@@ -331,6 +331,34 @@ def test_tensor_core_gemm_variants(nla, gpu, dtype, tc_bn):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float16])
+@pytest.mark.parametrize("cg", [1, 2])
+def test_cta_pair_kernel(nla, gpu, dtype, cg):
+    """The cta_group::2 kernel (csrc/gemm_tc2.cuh: a pair of CTAs shares one M = 256 tcgen05.mma) against the single-CTA kernel
+    and FP64 truth: updates with odd tile counts (a pair whose second CTA is past the last M tile), ragged N and K, every
+    majorness instantiation, and a full solve / multiply with the pairs forced on."""
+    import torch
+
+    rng = np.random.RandomState(11)
+    gpu.set_option("tc_cg", cg)
+    try:
+        for (M, N, K) in [(256, 256, 128), (384, 520, 320), (1000, 1544, 1096), (2048, 4096, 2048)]:
+            A = (rng.rand(M, K) - 0.5).astype(dtype); B = (rng.rand(K, N) - 0.5).astype(dtype); C = rng.rand(M, N).astype(dtype)
+            want = C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)
+            for ta, tb in (("N", "N"), ("T", "N"), ("N", "T")):
+                Ain = np.asfortranarray(A.T.copy() if ta == "T" else A); Bin = np.asfortranarray(B.T.copy() if tb == "T" else B)
+                dC = nla.colmajor(np.asfortranarray(C))
+                nla._gemm(dC, nla.colmajor(Ain), nla.colmajor(Bin), -1, transa=ta, transb=tb); torch.cuda.synchronize()
+                assert rel(nla.to_numpy(dC), want) < (2e-5 if dtype == np.float32 else 1e-3), (M, N, K, ta, tb)
+        n, m = 1160, 520
+        for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=5, recipe="scaled")
+            got = run_gpu(nla, side, uplo, trans, 1.5, func, A, B0)
+            assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (side, uplo, trans, func)
+    finally:
+        gpu.set_option("tc_cg", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
 def test_tensor_core_path_matches_simt_path(nla, gpu, dtype):
     """The tcgen05 path and the generic strided kernels (option force_simt) are two independent implementations of the same
     schedule: they must agree to rounding, for every side/uplo/trans/func, with alpha != 1 and a ragged order."""

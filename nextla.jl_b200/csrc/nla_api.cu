@@ -545,7 +545,6 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
       if (ctx->diag_ws_bytes < need) {
         if (ctx->diag_ws) cudaFree(ctx->diag_ws);
         ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
-  ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
         NLA_CUDA(ctx, cudaMalloc(&ctx->diag_ws, need));
         ctx->diag_ws_bytes = need;
       }
@@ -783,6 +782,7 @@ int nla_create(nla_handle_t* handle, int device) {
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
+  ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--m", type=int, default=M_PER_GPU, help="override RHS per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="N > 1: one blocking broadcast of A before the solve instead of the panel pipeline")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("NLA_STREAMS", "0")), help="0 = library default")
     return ap.parse_args()
 
@@ -166,9 +167,17 @@ def main():
     X = torch.empty((m, n), dtype=dt, device=dev).t()
     A_store = A.t()  # contiguous (n x n) storage for the broadcast
 
+    from importlib import import_module
+    sharded = import_module(nla.__name__ + ".sharded")
+
     def step():
+        # the only exchange: A from its owner to every GPU (NCCL over NVLink/NVSwitch).  Default: column panels of A in the order the
+        # schedule consumes them, on a side stream, the solve gated per panel (nla_rectrxm_gated) -> the broadcast hides behind the solve
+        if world > 1 and not args.no_pipeline:
+            sharded.unified_rectrxm_pipelined("L", "L", "N", 1.0, "S", A, X, src=0, panels=8, handle=h)
+            return
         if world > 1:
-            dist.broadcast(A_store, src=0)  # the only exchange: A from its owner to every GPU (NCCL over NVLink)
+            dist.broadcast(A_store, src=0)
         nla.unified_rectrxm("L", "L", "N", 1.0, "S", A, X, handle=h)
 
     def sync_all():
@@ -319,7 +328,8 @@ def main():
                 "config": {"workload": f"Float64 left/lower/no-trans TRSM via unified_rectrxm!, A {n}x{n}, {m} RHS per GPU (BASELINE configs[1])",
                            "n": n, "rhs_per_gpu": m, "rhs_total": m * world, "alpha": 1.0, "inputs": "scaled recipe (SURVEY 8(d)), seed 1235/777+rank",
                            "l2": "inputs (A 2 GiB + B 2 GiB per GPU) larger than L2; B restored from a pristine copy between steps outside the timed events",
-                           "parallelism": f"rhs-sharded x{world}, A broadcast by NCCL inside every step" if world > 1 else "single GPU",
+                           "parallelism": (f"rhs-sharded x{world}, A broadcast by NCCL inside every step "
+                                           + ("(one blocking broadcast)" if args.no_pipeline else "(8 column panels pipelined with the solve)")) if world > 1 else "single GPU",
                            "streams": args.streams or "auto", "leaf": h.get_option("leaf"), "macro": h.get_option("macro")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "backward_error": berr, "tolerance": 1e-13, "wall_ms_per_step_incl_restore": t_wall / args.steps * 1e3,

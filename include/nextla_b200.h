@@ -54,6 +54,19 @@ int nla_rectrxm(nla_handle_t handle, char side, char uplo, char trans, char func
 int nla_rectrxm_host(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
                      double alpha, const void *A_host, int64_t lda, void *B_host, int64_t ldb);
 
+/* Multi-GPU: the right-hand sides are sharded across GPUs and A is broadcast from its owner.  So that the
+ * broadcast overlaps the solve, A may arrive in panels of `panel_cols` columns: panel p = columns [p*panel_cols, (p+1)*panel_cols),
+ * and panel_events[p] is a cudaEvent_t recorded (on any stream of this device) after the copy / ncclBroadcast that fills it.
+ * The schedule makes `stream` wait for a panel's event right before the first launch that reads it.  (The Float32/Float16 path
+ * prepares the whole diagonal first and therefore waits for every panel up front.)  The reference has no multi-device path.
+ * nla_panel_order: host-only, the order in which the schedule first touches the panels = the order to broadcast them in;
+ * writes up to max_panels indices and returns the number of panels (or a negative nla_status). */
+int nla_rectrxm_gated(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
+                      double alpha, const void *A, int64_t lda, void *B, int64_t ldb, void *stream, int64_t panel_cols,
+                      int64_t n_panels, void *const *panel_events);
+int64_t nla_panel_order(char side, char uplo, char trans, char func, int64_t n, int64_t panel_cols, int64_t *order,
+                        int64_t max_panels);
+
 /* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
  * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
  * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */
@@ -80,6 +93,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "tc_chunk_k"  Float32: K extent accumulated in tensor memory before it is added into C with round-to-nearest (default 512; 0 = never)
  *   "trmm_batched" Float32/Float16 multiply: 1 (default) = out-of-place batched schedule (one copy of B in the handle's workspace, all diagonal
  *                 blocks in one launch, one triangular GEMM), 0 = the reference's in-place recursion
+ *   "inv_block"   Float32/Float16 solve: order of the diagonal blocks that are inverted once per call (FP64 128-blocks doubled in the next
+ *                 wider type) so that a leaf is ONE triangular tcgen05 GEMM: 0 = default (1024), 128 = plain 128-wide leaves, powers of two up to 4096
  *   "pdl"         1 (default) = launch the tcgen05 kernels with programmatic dependent launch (prologue overlaps the predecessor's tail)
  *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);

@@ -54,6 +54,8 @@ def load_library():
         "nla_version": (I, []),
         "nla_rectrxm": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
         "nla_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L]),
+        "nla_rectrxm_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P, L, L, c.POINTER(c.c_void_p)]),
+        "nla_panel_order": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
         "nla_trsm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
         "nla_trmm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
         "nla_leaf_max": (L, [I]),
@@ -73,6 +75,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
+            "nla_rectrxm_gated", "nla_panel_order",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 
@@ -207,6 +210,38 @@ def unified_rectrxm(side: str, uplo: str, transpose: str, alpha: float, func: st
         raise NextLAError("dimension mismatch between A and B")
     rc = load_library().nla_rectrxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
                                     _stream_ptr(stream))
+    _check(rc, h._h)
+    return B
+
+
+def panel_order(side: str, uplo: str, transpose: str, func: str, n: int, panel_cols: int):
+    """Host-only: the order in which the schedule first reads the column panels of A (panel p = columns [p*panel_cols, ...)),
+    i.e. the order in which a pipelined broadcast should deliver them."""
+    lib = load_library()
+    cnt = lib.nla_panel_order(_ch(side), _ch(uplo), _ch(transpose), _ch(func), n, panel_cols, None, 0)
+    if cnt < 0:
+        _check(-cnt)
+    buf = (ctypes.c_int64 * max(cnt, 1))()
+    lib.nla_panel_order(_ch(side), _ch(uplo), _ch(transpose), _ch(func), n, panel_cols, buf, cnt)
+    return [int(buf[i]) for i in range(cnt)]
+
+
+def unified_rectrxm_gated(side: str, uplo: str, transpose: str, alpha: float, func: str, A, B, panel_cols: int, panel_events, stream=None,
+                          handle: Optional[Handle] = None):
+    """unified_rectrxm with A arriving in column panels: `panel_events[p]` is a recorded torch.cuda.Event marking panel p
+    (columns [p*panel_cols, (p+1)*panel_cols)) valid; the schedule waits for a panel right before the first launch reading it."""
+    h = handle or default_handle(A.device.index)
+    pa, ar, ac, lda, dta = _desc(A)
+    pb, br, bc, ldb, dtb = _desc(B)
+    if dta != dtb or ar != ac:
+        raise NextLAError("A must be square and share B's element type")
+    n = ar
+    m = bc if side == "L" else br
+    if (side == "L" and br != n) or (side == "R" and bc != n):
+        raise NextLAError("dimension mismatch between A and B")
+    evs = (ctypes.c_void_p * len(panel_events))(*[ctypes.c_void_p(e.cuda_event) for e in panel_events])
+    rc = load_library().nla_rectrxm_gated(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
+                                          _stream_ptr(stream), int(panel_cols), len(panel_events), evs)
     _check(rc, h._h)
     return B
 

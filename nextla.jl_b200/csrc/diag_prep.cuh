@@ -24,17 +24,25 @@ constexpr int DP_LP = DP_B + 1;
 constexpr int DP_THREADS = 1024, DP_SPLIT = DP_THREADS / DP_B;   // lanes per column
 constexpr int DP_SMEM_BYTES = DP_B * DP_LP * 4 + DP_B * DP_LP * 8;
 
-template <typename T>
+template <typename TO> __device__ __forceinline__ void dp_store(TO* p, double v);
+template <> __device__ __forceinline__ void dp_store<double>(double* p, double v) { *p = v; }
+template <> __device__ __forceinline__ void dp_store<float>(float* p, double v) { *p = (float)v; }
+template <> __device__ __forceinline__ void dp_store<__half>(__half* p, double v) { *p = __float2half_rn((float)v); }
+
+// TO = element type of the workspace: T itself (128-wide leaves consume W directly), or the accumulation type of the block-inverse
+// doubling (tri_inv.cuh), which places block b at rows [128b, 128b+128), local columns [(128b) mod ib, +128) of a pitch-`ib` workspace.
+template <typename T, typename TO = T>
 struct DiagPrepParams {
   const T* A; long long t_rs, t_cs;   // Teff(r,k) = A[r*t_rs + k*t_cs]
   int n;                              // order of Teff
   int lower, solve;
   int block0;                         // first diagonal block handled by this launch (block b = blockIdx.x + block0)
-  T* W;                               // K-major workspace, 128 x 128 per block
+  TO* W;                              // K-major workspace, 128 x 128 per block
+  int pitch, ib;                      // elements between consecutive rows of W; order of the enclosing inverse block (128: none)
 };
 
-template <typename T>
-__global__ void __launch_bounds__(DP_THREADS) diag_prep_kernel(const DiagPrepParams<T> p) {
+template <typename T, typename TO = T>
+__global__ void __launch_bounds__(DP_THREADS) diag_prep_kernel(const DiagPrepParams<T, TO> p) {
   extern __shared__ __align__(16) uint8_t dp_smem[];
   float* Ls = reinterpret_cast<float*>(dp_smem);                       // [r][k], pitch DP_LP (normalised to lower)
   double* Xs = reinterpret_cast<double*>(dp_smem + DP_B * DP_LP * 4);  // [r][j], pitch DP_LP
@@ -81,15 +89,15 @@ __global__ void __launch_bounds__(DP_THREADS) diag_prep_kernel(const DiagPrepPar
   __syncthreads();
 
   // ---- store K-major (k contiguous), reversing back for upper blocks ----
-  T* Wb = p.W + (long long)off * DP_B;
+  TO* Wb = p.W + (long long)off * p.pitch + (off % p.ib);
   for (int e = tid; e < DP_B * DP_B; e += DP_THREADS) {
     const int k = e % DP_B, r = e / DP_B;
-    float v = 0.f;
+    double vd = 0.0;
     if (r < t && k < t) {
       const int rr = p.lower ? r : t - 1 - r, kk = p.lower ? k : t - 1 - k;   // position in the normalised (lower) block
-      if (kk <= rr) v = (float)Xs[rr * DP_LP + kk];
+      if (kk <= rr) vd = Xs[rr * DP_LP + kk];
     }
-    Traits<T>::st(Wb + (long long)r * DP_B + k, v);
+    dp_store<TO>(Wb + (long long)r * p.pitch + k, vd);
   }
 }
 

@@ -79,10 +79,15 @@ struct GemmTcParams {
   // K window per tile (batched TRMM, see nla_api.cu): t = tile index along M (or along N when win_on_n; N tile must be 128)
   //   win_mode 0: k in [0, K)                          1: diagonal block, k in [128t, 128t+128) of the V operand, [0,128) of the other
   //            2: k in [0, 128t)  (strictly below)     3: k in [128(t+1), K)  (strictly above)
+  //            4: k in [0, 128(t+1))  (lower triangle with its diagonal block: block-inverse leaves, tri_inv.cuh)     5: k in [128t, K)  (upper)
   int win_mode, win_on_n, win_shift_a;
   unsigned long long* dbg;   // optional: 8 globaltimer stamps per CTA (probe builds; nullptr in production)
   int chunk_k;        // Float32: K extent accumulated in TMEM before it is promoted into C (0 = everything in one chunk)
   int tiles_m, tiles_n;
+  // optional second destination for a sub-block of the final C (block-inverse leaves, nla_api.cu): C rows [dup_r0, +dup_rn) x
+  // columns [dup_c0, +dup_cn) are also stored column-major at dup (leading dimension dup_ld)
+  void* dup; long long dup_ld;
+  int dup_r0, dup_rn, dup_c0, dup_cn;
 };
 
 // instruction descriptor: FP32 accumulate, A/B format, majorness (0 = K-major, 1 = MN-major), N >> 3, M >> 4
@@ -135,7 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // K window of this tile
   int kbeg = 0, klen = p.K, ash = 0, bsh = 0;
   if (p.win_mode) {
-    if (p.win_mode == 2) {   // work grows with the tile index: start the heaviest tiles first
+    if (p.win_mode == 2 || p.win_mode == 4) {   // work grows with the tile index: start the heaviest tiles first
       if (p.win_on_n) tn = p.tiles_n - 1 - tn; else tm = p.tiles_m - 1 - tm;
     }
     const int t = p.win_on_n ? tn : tm;
@@ -144,6 +149,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (p.win_shift_a) ash = 128 * t; else bsh = 128 * t;
     } else if (p.win_mode == 2) {
       klen = min(p.K, 128 * t);
+    } else if (p.win_mode == 4) {
+      klen = min(p.K, 128 * (t + 1));
+    } else if (p.win_mode == 5) {
+      kbeg = 128 * t;
+      klen = p.K - kbeg;
     } else {
       kbeg = 128 * (t + 1);
       klen = p.K - kbeg;
@@ -372,6 +382,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else {
 #pragma unroll
               for (int e = 0; e < VEC; e++) if (grow + e < p.M) dst[e] = outv[e];
+            }
+            if (last && p.dup) {   // second copy of the rows/columns the next block-inverse leaf reads (its GEMM is out of place)
+              const int dr = grow - p.dup_r0, dc = tn * BN + col - p.dup_c0;
+              if (dr >= 0 && dr < p.dup_rn && dc >= 0 && dc < p.dup_cn) {
+                T* dd = reinterpret_cast<T*>(p.dup) + dr + (long long)dc * p.dup_ld;
+                if (grow + VEC <= p.M && dr + VEC <= p.dup_rn) {
+                  *reinterpret_cast<uint4*>(dd) = *reinterpret_cast<const uint4*>(outv);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < VEC; e++) if (grow + e < p.M && dr + e < p.dup_rn) dd[e] = outv[e];
+                }
+              }
             }
           }
         }

@@ -288,6 +288,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < VEC; e++) if (grow + e < p.M) dst[e] = outv[e];
             }
+            if (last && p.dup) {   // second copy of the rows/columns the next block-inverse leaf reads (its GEMM is out of place)
+              const int dr = grow - p.dup_r0, dc = tn * BN + col - p.dup_c0;
+              if (dr >= 0 && dr < p.dup_rn && dc >= 0 && dc < p.dup_cn) {
+                T* dd = reinterpret_cast<T*>(p.dup) + dr + (long long)dc * p.dup_ld;
+                if (grow + VEC <= p.M && dr + VEC <= p.dup_rn) {
+                  *reinterpret_cast<uint4*>(dd) = *reinterpret_cast<const uint4*>(outv);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < VEC; e++) if (grow + e < p.M && dr + e < p.dup_rn) dd[e] = outv[e];
+                }
+              }
+            }
           }
         }
       }

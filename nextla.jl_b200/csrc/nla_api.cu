@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "diag_prep.cuh"
+#include "tri_inv.cuh"
 
 using namespace nla;
 
@@ -50,7 +51,13 @@ struct nla_context {
   void* diag_ws; size_t diag_ws_bytes;
   void* bcopy_ws; size_t bcopy_ws_bytes;   // pristine copy of B for the batched (out-of-place) TRMM
   int64_t trmm_batched;
+  int64_t inv_block;    // order of the inverted diagonal blocks of the Float32/Float16 solve (0 = default)
+  void* inv_acc; size_t inv_acc_bytes;     // block inverses / phase-1 products in the accumulation type (tri_inv.cuh)
+  void* inv_u; size_t inv_u_bytes;
   int64_t pdl;
+  int64_t inv_overlap;  // 1 = invert all but the first two blocks on a side stream while the solve is running
+  cudaStream_t prep_stream; cudaEvent_t prep_event;
+  int64_t inv_dup;      // 1 = updates also write the next leaf's block of V into the leaf workspace (0: explicit copy per leaf)
   int64_t tc_dbg;       // device pointer to per-CTA timing stamps (probes only)
   // device staging for the host-buffer entry point
   void* stage_a; size_t stage_a_bytes;
@@ -353,17 +360,18 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
   return NLA_ERR_UNSUPPORTED;
 }
 
-template <typename T>
+template <typename T, typename TO = T>
 static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t t_cs, int64_t n, bool lower, bool solve, int64_t block0,
-                            int64_t nblocks, T* W, cudaStream_t st) {
+                            int64_t nblocks, TO* W, cudaStream_t st, int64_t ib = DP_B) {
   static bool configured[64] = {false};
   if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(diag_prep_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES));
+    NLA_CUDA(ctx, (cudaFuncSetAttribute(diag_prep_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES)));
     configured[ctx->device & 63] = true;
   }
-  DiagPrepParams<T> dp;
+  DiagPrepParams<T, TO> dp;
   dp.A = A; dp.t_rs = t_rs; dp.t_cs = t_cs; dp.n = (int)n; dp.lower = lower; dp.solve = solve; dp.block0 = (int)block0; dp.W = W;
-  diag_prep_kernel<T><<<(unsigned)nblocks, DP_THREADS, DP_SMEM_BYTES, st>>>(dp);
+  dp.pitch = (int)ib; dp.ib = (int)ib;
+  diag_prep_kernel<T, TO><<<(unsigned)nblocks, DP_THREADS, DP_SMEM_BYTES, st>>>(dp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
@@ -380,11 +388,30 @@ struct TmaMaps {
   int majT, majV;
   CUtensorMap mapW;
   CUtensorMap mapT128, mapV128, mapW128;   // B-operand maps for the 128-wide N tile (whichever of T / V / W plays that role)
+  // block-inverse solve leaves (tri_inv.cuh): order of the inverted blocks (128 = plain tensor-core leaves) and the maps of the
+  // copy of the leaf's block of V (the leaf GEMM is out of place); `Last` = the ragged last block (its K extent is the map's bound)
+  int64_t ib, ws_ld;
+  int64_t late0, late1;   // ib-blocks [late0, late1) are being inverted on the side stream: wait for prep_event before their first leaf
+  CUtensorMap mapS, mapS128, mapSLast, mapSLast128;
 };
+
+// accumulation type of the block-inverse doubling: one step wider than the element type
+template <typename T> struct InvAcc { using type = float; };
+template <> struct InvAcc<float> { using type = double; };
+
+static int grow_ws(nla_context* ctx, void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return NLA_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  NLA_CUDA(ctx, cudaMalloc(ptr, need));
+  *have = need;
+  return NLA_OK;
+}
 
 // One update  V[c-range] <- post*(beta*V[c-range] + sgn*Teff[c-range,k-range]*V[k-range])  for vectors [v0, v0+nv)
 template <typename T>
-static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st,
+                         const Op* dup_leaf = nullptr) {
   const double sgn = P.solve ? -1.0 : 1.0;
   const T* A = (const T*)P.A;
   T* B = (T*)P.B;
@@ -393,6 +420,12 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
       GemmTcParams gp{};
       gp.beta = (float)o.pre; gp.sgn = (float)sgn; gp.post = (float)o.post; gp.overwrite = 0; gp.ldc = P.ldb;
       gp.K = (int)o.kn;
+      if (dup_leaf) {   // the block of V the next (block-inverse) leaf reads is also written into the leaf's workspace
+        T* ws = (T*)ctx->bcopy_ws;
+        gp.dup_ld = maps.ws_ld;
+        if (!P.right) { gp.dup = ws + v0 * maps.ws_ld; gp.dup_r0 = (int)(dup_leaf->off - o.c0); gp.dup_rn = (int)dup_leaf->sz; gp.dup_c0 = 0; gp.dup_cn = (int)nv; }
+        else { gp.dup = ws + v0; gp.dup_r0 = 0; gp.dup_rn = (int)nv; gp.dup_c0 = (int)(dup_leaf->off - o.c0); gp.dup_cn = (int)dup_leaf->sz; }
+      }
       if (!P.right) {   // C = V[c-range, v-range]; A operand = Teff block, B operand = V[k-range, v-range] (K-major)
         gp.M = (int)o.cn; gp.N = (int)nv;
         gp.a_mn0 = (int)o.c0; gp.a_k0 = (int)o.k0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.k0;
@@ -465,7 +498,8 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
 // Tensor-core leaf (Float32 / Float16): V_blk <- (pre*post) * P * V_blk with P = prepared diagonal block (diag_prep.cuh).
 // In place: a CTA reads exactly the rows/columns of V it later overwrites (K covers the whole block), after all its MMAs.
 template <typename T>
-static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
+static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st,
+                          bool copied = false) {
   if (maps.prep_per_leaf) {
     const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
     int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, o.off / DP_B, 1, (T*)ctx->diag_ws, st);
@@ -475,6 +509,32 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
   gp.beta = 0.f; gp.sgn = 1.f; gp.post = (float)(o.pre * o.post); gp.overwrite = 1; gp.ldc = P.ldb;
   gp.K = (int)o.sz;
   T* B = (T*)P.B;
+  if (maps.ib > DP_B) {
+    // X_blk = inv(Teff_blk) * V_blk, one triangular GEMM per block (per-tile K window).  Out of place: a tile needs rows of V
+    // that other tiles overwrite, so the block of V is first copied into the handle's workspace.
+    const bool last = o.sz < maps.ib;
+    T* ws = (T*)ctx->bcopy_ws;
+    gp.win_mode = P.lower ? 4 : 5;
+    if (copied) {
+      // the preceding update has already written this block of V into the workspace (GemmTcParams::dup)
+    } else if (!P.right) {
+      NLA_CUDA(ctx, cudaMemcpy2DAsync(ws + v0 * maps.ws_ld, (size_t)maps.ws_ld * sizeof(T), B + o.off + v0 * P.ldb, (size_t)P.ldb * sizeof(T),
+                                      (size_t)o.sz * sizeof(T), (size_t)nv, cudaMemcpyDeviceToDevice, st));
+    } else {
+      NLA_CUDA(ctx, cudaMemcpy2DAsync(ws + v0, (size_t)maps.ws_ld * sizeof(T), B + v0 + o.off * P.ldb, (size_t)P.ldb * sizeof(T),
+                                      (size_t)nv * sizeof(T), (size_t)o.sz, cudaMemcpyDeviceToDevice, st));
+    }
+    if (!P.right) {
+      gp.M = (int)o.sz; gp.N = (int)nv; gp.win_on_n = 0;
+      gp.a_mn0 = (int)o.off; gp.a_k0 = 0; gp.b_mn0 = (int)v0; gp.b_k0 = 0;
+      gp.C = B + o.off + v0 * P.ldb;
+      return launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, last ? maps.mapSLast : maps.mapS, last ? maps.mapSLast128 : maps.mapS128, gp, st);
+    }
+    gp.M = (int)nv; gp.N = (int)o.sz; gp.win_on_n = 1;
+    gp.a_mn0 = (int)v0; gp.a_k0 = 0; gp.b_mn0 = (int)o.off; gp.b_k0 = 0;
+    gp.C = B + v0 + o.off * P.ldb;
+    return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, last ? maps.mapSLast : maps.mapS, maps.mapW, maps.mapW128, gp, st, 128);
+  }
   if (!P.right) {
     gp.M = (int)o.sz; gp.N = (int)nv;
     gp.a_mn0 = (int)o.off; gp.a_k0 = 0; gp.b_mn0 = (int)v0; gp.b_k0 = (int)o.off;
@@ -487,9 +547,40 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
   return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, maps.mapV, maps.mapW, maps.mapW128, gp, st);
 }
 
+// Pipelined arrival of A (nla_rectrxm_gated): A becomes valid in panels of `panel_cols` columns; events[p] marks panel p.
+struct Gate { int64_t panel_cols, n_panels; cudaEvent_t const* events; };
+
+// columns of A an op reads: a leaf its diagonal block, an update the block Teff[c-range, k-range] = A[c,k] or A[k,c]
+static void op_columns(const Problem& P, const Op& o, int64_t& c0, int64_t& c1) {
+  if (o.kind == Op::LEAF) { c0 = o.off; c1 = o.off + o.sz; }
+  else if (P.teff_trans) { c0 = o.c0; c1 = o.c0 + o.cn; }
+  else { c0 = o.k0; c1 = o.k0 + o.kn; }
+}
+
+static int gate_wait(nla_context* ctx, const Gate* gate, std::vector<char>& waited, int64_t c0, int64_t c1, cudaStream_t st) {
+  if (!gate || c1 <= c0) return NLA_OK;
+  for (int64_t p = c0 / gate->panel_cols; p <= (c1 - 1) / gate->panel_cols && p < gate->n_panels; p++) {
+    if (waited[(size_t)p]) continue;
+    NLA_CUDA(ctx, cudaStreamWaitEvent(st, gate->events[p], 0));
+    waited[(size_t)p] = 1;
+  }
+  return NLA_OK;
+}
+
 template <typename T>
-static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st) {
-  for (const Op& o : ops) {
+static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, const std::vector<Op>& ops, int64_t v0, int64_t nv, cudaStream_t st,
+                   const Gate* gate = nullptr) {
+  std::vector<char> waited(gate ? (size_t)gate->n_panels : 0, 0);
+  bool late_waited = false;
+  const Op* copied_leaf = nullptr;   // block-inverse leaf whose block of V the preceding update has already copied (GemmTcParams::dup)
+  for (size_t oi = 0; oi < ops.size(); oi++) {
+    const Op& o = ops[oi];
+    if (gate) {
+      int64_t c0, c1;
+      op_columns(P, o, c0, c1);
+      int grc = gate_wait(ctx, gate, waited, c0, c1, st);
+      if (grc != NLA_OK) return grc;
+    }
     nla_context::ProfRec pr{};
     if (ctx->profile) {
       for (cudaEvent_t* e : {&pr.e0, &pr.e1}) {
@@ -501,9 +592,18 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
     }
     int rc;
     if (o.kind == Op::GEMM) {
-      rc = launch_update<T>(ctx, P, maps, o, v0, nv, st);
+      const Op* dup = nullptr;
+      if (maps.tc && maps.ib > DP_B && ctx->inv_dup && oi + 1 < ops.size() && ops[oi + 1].kind == Op::LEAF && ops[oi + 1].off >= o.c0 &&
+          ops[oi + 1].off + ops[oi + 1].sz <= o.c0 + o.cn)
+        dup = &ops[oi + 1];
+      rc = launch_update<T>(ctx, P, maps, o, v0, nv, st, dup);
+      copied_leaf = dup;
     } else if (maps.tc) {
-      if constexpr (!std::is_same<T, double>::value) rc = launch_leaf_tc<T>(ctx, P, maps, o, v0, nv, st);
+      if (!late_waited && maps.late1 > maps.late0 && o.off / maps.ib >= maps.late0 && o.off / maps.ib < maps.late1) {
+        NLA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->prep_event, 0));
+        late_waited = true;
+      }
+      if constexpr (!std::is_same<T, double>::value) rc = launch_leaf_tc<T>(ctx, P, maps, o, v0, nv, st, copied_leaf == &o);
       else rc = NLA_ERR_UNSUPPORTED;
     } else if (maps.fused) {
       rc = launch_slab(ctx, P, maps, o, v0, nv, st);
@@ -526,12 +626,21 @@ struct Plan {
   TmaMaps maps;
 };
 
+// Order of the inverted diagonal blocks of a Float32/Float16 solve: option "inv_block", default 1024 (measured),
+// never more than the smallest power of two covering n.
+static int64_t pick_inv_block(nla_context* ctx, const Problem& P, bool allow) {
+  if (!allow || !P.solve || P.n <= DP_B) return DP_B;
+  int64_t ib = ctx->inv_block > 0 ? ctx->inv_block : 1024;
+  while (ib > DP_B && ib / 2 >= P.n) ib /= 2;
+  return ib;
+}
+
 template <typename T>
-static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
+static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, bool allow_inv = true) {
   const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
   std::vector<Op>& ops = plan.ops;
   TmaMaps& maps = plan.maps;
-  maps.ok = false; maps.fused = false; maps.tc = false; maps.prep_per_leaf = false;
+  maps.ok = false; maps.fused = false; maps.tc = false; maps.prep_per_leaf = false; maps.ib = DP_B; maps.ws_ld = 0; maps.late0 = maps.late1 = 0;
 
   // FP64 tensor-core path: both matrices must satisfy the TMA constraints (16-byte aligned base, even leading dimension,
   // row counts that are multiples of 8); otherwise the generic strided kernels take the call.
@@ -541,24 +650,42 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan) {
     // base and column pitch); cutoff = 128 = the M tile of one tcgen05.mma.  Otherwise the generic strided kernels.
     if (!ctx->force_simt && ctx->encode && tc_ok<T>(P.A, P.n, P.n, P.lda) && tc_ok<T>(P.B, brows, bcols, P.ldb)) {
       const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
-      const size_t need = (size_t)nblocks * DP_B * DP_B * sizeof(T);
-      if (ctx->diag_ws_bytes < need) {
-        if (ctx->diag_ws) cudaFree(ctx->diag_ws);
-        ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
-        NLA_CUDA(ctx, cudaMalloc(&ctx->diag_ws, need));
-        ctx->diag_ws_bytes = need;
+      const int64_t ib = pick_inv_block(ctx, P, allow_inv);   // 128: the prepared 128-blocks are the leaves' operands
+      using Acc = typename InvAcc<T>::type;
+      int wrc = grow_ws(ctx, &ctx->diag_ws, &ctx->diag_ws_bytes, (size_t)nblocks * DP_B * ib * sizeof(T));
+      if (wrc != NLA_OK) return wrc;
+      bool ok = true;
+      if (ib > DP_B) {
+        if ((wrc = grow_ws(ctx, &ctx->inv_acc, &ctx->inv_acc_bytes, (size_t)nblocks * DP_B * ib * sizeof(Acc))) != NLA_OK) return wrc;
+        if ((wrc = grow_ws(ctx, &ctx->inv_u, &ctx->inv_u_bytes, (size_t)nblocks * DP_B * ib * sizeof(Acc))) != NLA_OK) return wrc;
+        // copy of one block of V: ib x m (left side, pitch ib) or m x ib (right side, pitch m rounded up to 16 elements)
+        maps.ws_ld = P.right ? ((P.m + 15) & ~15ll) : ib;
+        const size_t need = (size_t)(P.right ? maps.ws_ld * ib : ib * P.m) * sizeof(T);
+        if ((wrc = grow_ws(ctx, &ctx->bcopy_ws, &ctx->bcopy_ws_bytes, need)) != NLA_OK) return wrc;
+        const int64_t lastsz = P.n % ib ? P.n % ib : ib;
+        if (!P.right) {
+          ok = encode_map_tc<T>(ctx, &maps.mapS, ctx->bcopy_ws, ib, P.m, ib, MAJ_K, false) &&
+               encode_map_tc<T>(ctx, &maps.mapS128, ctx->bcopy_ws, ib, P.m, ib, MAJ_K, false, 128) &&
+               encode_map_tc<T>(ctx, &maps.mapSLast, ctx->bcopy_ws, lastsz, P.m, ib, MAJ_K, false) &&
+               encode_map_tc<T>(ctx, &maps.mapSLast128, ctx->bcopy_ws, lastsz, P.m, ib, MAJ_K, false, 128);
+        } else {
+          ok = encode_map_tc<T>(ctx, &maps.mapS, ctx->bcopy_ws, P.m, ib, maps.ws_ld, MAJ_MN, true) &&
+               encode_map_tc<T>(ctx, &maps.mapSLast, ctx->bcopy_ws, P.m, lastsz, maps.ws_ld, MAJ_MN, true);
+          maps.mapS128 = maps.mapS; maps.mapSLast128 = maps.mapSLast;
+        }
       }
       maps.majT = P.teff_trans ? MAJ_K : MAJ_MN;   // Teff block: A operand (left side) / B operand (right side)
       maps.majV = !P.right ? MAJ_K : MAJ_MN;       // V: B operand (left side) / A operand (right side)
-      const bool ok = encode_map_tc<T>(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, maps.majT, !P.right) &&
-                      encode_map_tc<T>(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, maps.majV, P.right) &&
-                      encode_map_tc<T>(ctx, &maps.mapW, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right) &&
-                      encode_map_tc<T>(ctx, &maps.mapT128, P.A, P.n, P.n, P.lda, maps.majT, !P.right, 128) &&
-                      encode_map_tc<T>(ctx, &maps.mapV128, P.B, brows, bcols, P.ldb, maps.majV, P.right, 128) &&
-                      encode_map_tc<T>(ctx, &maps.mapW128, ctx->diag_ws, DP_B, nblocks * DP_B, DP_B, MAJ_K, !P.right, 128);
+      ok = ok && encode_map_tc<T>(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, maps.majT, !P.right) &&
+           encode_map_tc<T>(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, maps.majV, P.right) &&
+           encode_map_tc<T>(ctx, &maps.mapW, ctx->diag_ws, ib, nblocks * DP_B, ib, MAJ_K, !P.right) &&
+           encode_map_tc<T>(ctx, &maps.mapT128, P.A, P.n, P.n, P.lda, maps.majT, !P.right, 128) &&
+           encode_map_tc<T>(ctx, &maps.mapV128, P.B, brows, bcols, P.ldb, maps.majV, P.right, 128) &&
+           encode_map_tc<T>(ctx, &maps.mapW128, ctx->diag_ws, ib, nblocks * DP_B, ib, MAJ_K, !P.right, 128);
       if (ok) {
         maps.tc = true;
-        build_schedule(P, DP_B, 0, P.n, false, true, ops);
+        maps.ib = ib;
+        build_schedule(P, ib, 0, P.n, false, true, ops);
         return NLA_OK;
       }
     }
@@ -677,8 +804,40 @@ static int ensure_streams(nla_context* ctx, int64_t S) {
   return NLA_OK;
 }
 
+// Block inverses of order ib for a solve (tri_inv.cuh): 128-blocks in FP64 (diag_prep), log2(ib/128) doubling levels of two
+// batched launches each, one rounding pass into the element type.  All on `stream`, ahead of the schedule.
+// Only the ib-blocks [blk0, blk1): the first blocks the schedule needs are prepared on the caller's stream, the rest on a
+// side stream while the solve is already running (rectrxm_typed).
 template <typename T>
-static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream) {
+static int prepare_block_inverses(nla_context* ctx, const Problem& P, int64_t ib, cudaStream_t st, int64_t blk0, int64_t blk1) {
+  using Acc = typename InvAcc<T>::type;
+  const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
+  const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
+  const int64_t r0 = blk0 * ib, r1 = std::min(nblocks * DP_B, blk1 * ib);   // workspace rows of this range
+  if (r1 <= r0) return NLA_OK;
+  int rc = launch_diag_prep<T, Acc>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, true, r0 / DP_B, (r1 - r0) / DP_B, (Acc*)ctx->inv_acc, st, ib);
+  if (rc != NLA_OK) return rc;
+  TriInvParams<T, Acc> tp;
+  tp.A = (const T*)P.A; tp.t_rs = t_rs; tp.t_cs = t_cs; tp.n = (int)P.n; tp.ib = (int)ib; tp.lower = P.lower;
+  tp.W = (Acc*)ctx->inv_acc; tp.U = (Acc*)ctx->inv_u;
+  for (int64_t s = DP_B; s < ib; s *= 2) {
+    tp.s = (int)s;
+    const int64_t tiles = (s + TI_BM - 1) / TI_BM;
+    tp.pair0 = (int)(r0 / (2 * s));
+    dim3 grid((unsigned)(tiles * tiles), (unsigned)((std::min(P.n, r1) + 2 * s - 1) / (2 * s) - tp.pair0));
+    tri_inv_step_kernel<T, Acc, 1><<<grid, TI_THREADS, 0, st>>>(tp);
+    tri_inv_step_kernel<T, Acc, 2><<<grid, TI_THREADS, 0, st>>>(tp);
+    ctx->launches += 2;
+  }
+  const unsigned cgrid = (unsigned)std::min<int64_t>(((r1 - r0) * ib + 255) / 256, (int64_t)ctx->sm_count * 16);
+  tri_inv_convert_kernel<T, Acc><<<cgrid, 256, 0, st>>>((const Acc*)ctx->inv_acc, (T*)ctx->diag_ws, (int)P.n, (int)r0, (int)r1, (int)ib, P.lower ? 1 : 0);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+template <typename T>
+static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream, const Gate* gate = nullptr) {
   Plan plan;
   int prc = make_plan<T>(ctx, P, plan);
   if (prc != NLA_OK) return prc;
@@ -686,8 +845,35 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   const TmaMaps& maps = plan.maps;
   if constexpr (!std::is_same<T, double>::value) {
     if (maps.tc) {  // prepare every diagonal block once, ahead of the schedule (and of the fork into RHS slabs)
+      if (gate) {   // the preparation reads the whole diagonal: all of A must have arrived
+        std::vector<char> waited((size_t)gate->n_panels, 0);
+        int grc = gate_wait(ctx, gate, waited, 0, P.n, stream);
+        if (grc != NLA_OK) return grc;
+        gate = nullptr;
+      }
       const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
-      int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream);
+      int rc;
+      if (maps.ib > DP_B) {
+        // the first two blocks the schedule consumes are inverted here; the others on a side stream, overlapped with the first
+        // leaves and updates (run_ops waits for prep_event before the first leaf that needs them)
+        const int64_t nb = (P.n + maps.ib - 1) / maps.ib, ga = 2;
+        if (ctx->inv_overlap && nb > ga + 1) {
+          if (!ctx->prep_stream) {
+            NLA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+            NLA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
+          }
+          const bool asc = P.lower;   // a solve with a lower Teff walks the diagonal forward
+          plan.maps.late0 = asc ? ga : 0; plan.maps.late1 = asc ? nb : nb - ga;
+          NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));
+          NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->fork_event, 0));
+          rc = prepare_block_inverses<T>(ctx, P, maps.ib, ctx->prep_stream, plan.maps.late0, plan.maps.late1);
+          if (rc != NLA_OK) return rc;
+          NLA_CUDA(ctx, cudaEventRecord(ctx->prep_event, ctx->prep_stream));
+          rc = prepare_block_inverses<T>(ctx, P, maps.ib, stream, asc ? 0 : nb - ga, asc ? ga : nb);
+        } else {
+          rc = prepare_block_inverses<T>(ctx, P, maps.ib, stream, 0, nb);
+        }
+      } else rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream);
       if (rc != NLA_OK) return rc;
       if (!P.solve && ctx->trmm_batched) return trmm_batched_tc<T>(ctx, P, maps, stream);
     }
@@ -700,7 +886,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   int64_t S = ctx->nstreams > 0 ? ctx->nstreams : maps.tc ? 1 : std::min<int64_t>(4, std::max<int64_t>(1, P.m / 4096));
   const int64_t gran = maps.tc ? 256 : 128;
   if (P.m < 2 * gran * S) S = std::max<int64_t>(1, P.m / (2 * gran));
-  if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream);
+  if (S == 1) return run_ops<T>(ctx, P, maps, ops, 0, P.m, stream, gate);
 
   { int erc = ensure_streams(ctx, S); if (erc != NLA_OK) return erc; }
   NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));
@@ -709,7 +895,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
     const int64_t v0 = s * per, nv = std::min(per, P.m - v0);
     if (nv <= 0) break;
     NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[s], ctx->fork_event, 0));
-    int rc = run_ops<T>(ctx, P, maps, ops, v0, nv, ctx->streams[s]);
+    int rc = run_ops<T>(ctx, P, maps, ops, v0, nv, ctx->streams[s], gate);
     if (rc != NLA_OK) return rc;
     NLA_CUDA(ctx, cudaEventRecord(ctx->events[s], ctx->streams[s]));
     NLA_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->events[s], 0));
@@ -741,11 +927,11 @@ static int make_problem(Problem& P, char side, char uplo, char trans, char func,
   return NLA_OK;
 }
 
-static int dispatch(nla_context* ctx, const Problem& P, cudaStream_t st) {
+static int dispatch(nla_context* ctx, const Problem& P, cudaStream_t st, const Gate* gate = nullptr) {
   switch (P.dtype) {
-    case NLA_F64: return rectrxm_typed<double>(ctx, P, st);
-    case NLA_F32: return rectrxm_typed<float>(ctx, P, st);
-    default: return rectrxm_typed<__half>(ctx, P, st);
+    case NLA_F64: return rectrxm_typed<double>(ctx, P, st, gate);
+    case NLA_F32: return rectrxm_typed<float>(ctx, P, st, gate);
+    default: return rectrxm_typed<__half>(ctx, P, st, gate);
   }
 }
 
@@ -783,6 +969,8 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
+  ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
+  ctx->inv_dup = 1; ctx->inv_block = 0; ctx->inv_acc = ctx->inv_u = nullptr; ctx->inv_acc_bytes = ctx->inv_u_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
@@ -809,6 +997,10 @@ int nla_destroy(nla_handle_t h) {
   if (h->stage_b) cudaFree(h->stage_b);
   if (h->diag_ws) cudaFree(h->diag_ws);
   if (h->bcopy_ws) cudaFree(h->bcopy_ws);
+  if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
+  if (h->prep_event) cudaEventDestroy(h->prep_event);
+  if (h->inv_acc) cudaFree(h->inv_acc);
+  if (h->inv_u) cudaFree(h->inv_u);
   h->magic = 0;
   delete h;
   return NLA_OK;
@@ -828,6 +1020,12 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
   if (!strcmp(key, "trmm_batched")) { h->trmm_batched = value != 0; return NLA_OK; }
   if (!strcmp(key, "pdl")) { h->pdl = value != 0; return NLA_OK; }
+  if (!strcmp(key, "inv_dup")) { h->inv_dup = value != 0; return NLA_OK; }
+  if (!strcmp(key, "inv_overlap")) { h->inv_overlap = value != 0; return NLA_OK; }
+  if (!strcmp(key, "inv_block")) {
+    if (value != 0 && (value < 128 || value > 4096 || (value & (value - 1)))) return NLA_ERR_INVALID_DIM;
+    h->inv_block = value; return NLA_OK;
+  }
   if (!strcmp(key, "tc_dbg")) { h->tc_dbg = value; return NLA_OK; }
   if (!strcmp(key, "tc_chunk_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_chunk_k = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
@@ -847,6 +1045,9 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "tc_chunk_k")) return h->tc_chunk_k;
   if (!strcmp(key, "trmm_batched")) return h->trmm_batched;
   if (!strcmp(key, "pdl")) return h->pdl;
+  if (!strcmp(key, "inv_block")) return h->inv_block;
+  if (!strcmp(key, "inv_dup")) return h->inv_dup;
+  if (!strcmp(key, "inv_overlap")) return h->inv_overlap;
   return -1;
 }
 
@@ -903,6 +1104,50 @@ int nla_rectrxm(nla_handle_t h, char side, char uplo, char trans, char func, int
   if (n == 0 || m == 0) return NLA_OK;
   NLA_CUDA(h, cudaSetDevice(h->device));
   return dispatch(h, P, (cudaStream_t)stream);
+}
+
+int nla_rectrxm_gated(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                      const void* A, int64_t lda, void* B, int64_t ldb, void* stream, int64_t panel_cols, int64_t n_panels,
+                      void* const* panel_events) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A, lda, B, ldb);
+  if (rc != NLA_OK) return rc;
+  if (panel_cols <= 0 || n_panels < 0 || n_panels * panel_cols < n) return NLA_ERR_INVALID_DIM;
+  if (n_panels > 0 && !panel_events) return NLA_ERR_NULL_POINTER;
+  for (int64_t p = 0; p < n_panels; p++) if (!panel_events[p]) return NLA_ERR_NULL_POINTER;
+  if (n == 0 || m == 0) return NLA_OK;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  Gate gate{panel_cols, n_panels, (cudaEvent_t const*)panel_events};
+  return dispatch(h, P, (cudaStream_t)stream, &gate);
+}
+
+int64_t nla_panel_order(char side, char uplo, char trans, char func, int64_t n, int64_t panel_cols, int64_t* order, int64_t max_panels) {
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, NLA_F64, n, 1, 1.0, (const void*)8, std::max<int64_t>(1, n), (void*)8, std::max<int64_t>(1, n));
+  if (rc != NLA_OK) return -rc;
+  if (panel_cols <= 0) return -NLA_ERR_INVALID_DIM;
+  if (n == 0) return 0;
+  const int64_t np = (n + panel_cols - 1) / panel_cols;
+  std::vector<Op> ops;
+  build_schedule(P, 128, 0, n, false, true, ops);   // first-touch order does not depend on the cutoff (it is monotone in the offset)
+  std::vector<char> seen((size_t)np, 0);
+  int64_t cnt = 0;
+  for (const Op& o : ops) {
+    int64_t c0, c1;
+    op_columns(P, o, c0, c1);
+    // panels in the direction this schedule walks the diagonal, so that a wide update asks for them in consumption order
+    const bool asc = (P.solve == P.lower);
+    const int64_t p0 = c0 / panel_cols, p1 = (c1 - 1) / panel_cols;
+    for (int64_t i = 0; i <= p1 - p0; i++) {
+      const int64_t p = asc ? p0 + i : p1 - i;
+      if (seen[(size_t)p]) continue;
+      seen[(size_t)p] = 1;
+      if (order && cnt < max_panels) order[cnt] = p;
+      cnt++;
+    }
+  }
+  return cnt;
 }
 
 static int leaf_entry(nla_handle_t h, bool solve, char side, char uplo, int dtype, int64_t n, int64_t m, const void* A, int64_t lda,
@@ -1034,9 +1279,10 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
   D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
   Plan plan;
   switch (dtype) {
-    case NLA_F64: rc = make_plan<double>(h, D, plan); break;
-    case NLA_F32: rc = make_plan<float>(h, D, plan); break;
-    default: rc = make_plan<__half>(h, D, plan); break;
+    // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived)
+    case NLA_F64: rc = make_plan<double>(h, D, plan, false); break;
+    case NLA_F32: rc = make_plan<float>(h, D, plan, false); break;
+    default: rc = make_plan<__half>(h, D, plan, false); break;
   }
   if (rc != NLA_OK) return rc;
   plan.maps.prep_per_leaf = plan.maps.tc;

@@ -48,3 +48,60 @@ def unified_rectrxm_sharded(side: str, uplo: str, transpose: str, alpha: float, 
     if not empty:
         solver(side, uplo, transpose, alpha, func, A, B_local)
     return B_local
+
+
+def panel_geometry(n: int, panels: int, gran: int = 128) -> Tuple[int, int]:
+    """(panel_cols, n_panels): about `panels` column panels of A, a multiple of `gran` columns wide."""
+    if n <= 0:
+        return gran, 0
+    pc = -(-n // max(1, panels))
+    pc = -(-pc // gran) * gran
+    return pc, -(-n // pc)
+
+
+def broadcast_panels(A_storage, order, panel_cols: int, src: int = 0, group=None, on_panel: Optional[Callable] = None):
+    """Broadcast A panel by panel in the given order.  `A_storage` is the contiguous (n x n) storage of a column-major A, so
+    column panel p of A is the row block [p*panel_cols, (p+1)*panel_cols) of the storage.  `on_panel(p)` runs after each
+    panel has been enqueued (the CUDA path records an event there)."""
+    import torch.distributed as dist
+
+    n = A_storage.shape[0]
+    for p in order:
+        dist.broadcast(A_storage[p * panel_cols:min(n, (p + 1) * panel_cols)], src=src, group=group)
+        if on_panel is not None:
+            on_panel(p)
+
+
+_side_streams = {}
+
+
+def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float, func: str, A, B_local, src: int = 0, group=None,
+                              panels: int = 8, handle=None):
+    """Multi-GPU call with the broadcast of A overlapped with the solve: A travels over NCCL in column
+    panels, in the order the schedule consumes them, on a side stream; the solve runs on the current stream and waits for
+    each panel right before the first kernel that reads it (nla_rectrxm_gated).  CUDA only."""
+    import torch
+    import torch.distributed as dist
+
+    from . import panel_order, unified_rectrxm, unified_rectrxm_gated
+
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return unified_rectrxm(side, uplo, transpose, alpha, func, A, B_local, handle=handle)
+    n = A.shape[0]
+    if not (A.dim() == 2 and A.stride(0) == 1 and A.stride(1) == n):
+        raise ValueError("pipelined broadcast needs a column-major A with leading dimension n")
+    pc, npan = panel_geometry(n, panels)
+    order = panel_order(side, uplo, transpose, func, n, pc)
+    dev = A.device
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(device=dev)
+    bs = _side_streams[dev]
+    events = [torch.cuda.Event() for _ in range(npan)]
+    bs.wait_stream(torch.cuda.current_stream(dev))   # earlier work on the caller's stream may still be using A
+    with torch.cuda.stream(bs):
+        broadcast_panels(A.t(), order, pc, src=src, group=group, on_panel=lambda p: events[p].record(bs))
+    empty = B_local.shape[1] == 0 if side == "L" else B_local.shape[0] == 0
+    if empty:
+        torch.cuda.current_stream(dev).wait_stream(bs)
+        return B_local
+    return unified_rectrxm_gated(side, uplo, transpose, alpha, func, A, B_local, pc, events, handle=handle)

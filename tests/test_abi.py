@@ -1,6 +1,7 @@
 """CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol declared in
 include/nextla_b200.h, reports errors as status codes, and its host-side schedule equals the reference's recursion."""
 import ctypes
+import itertools
 import os
 import re
 
@@ -118,3 +119,21 @@ def test_bad_arguments_return_status_codes(nla):
     assert lib.nla_plan(b"X", b"L", b"N", b"S", 8, 0, None, 0) == -1
     assert lib.nla_plan(b"L", b"L", b"N", b"S", -1, 0, None, 0) == -2
     assert lib.nla_plan(b"L", b"L", b"N", b"S", 0, 0, None, 0) == 0
+
+
+def test_panel_order_follows_the_schedule(nla):
+    """nla_panel_order (host-only): the column panels of A in the order the schedule first reads them -- ascending when the
+    schedule walks the diagonal forward, descending otherwise; every panel exactly once; consistent with nla_plan."""
+    n, pc = 4096, 512
+    for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+        order = nla.panel_order(side, uplo, trans, func, n, pc)
+        assert sorted(order) == list(range(n // pc)), (side, uplo, trans, func)
+        # first leaf of the flattened recursion tells the direction
+        first = [op for op in nla.plan(side, uplo, trans, func, n, 128) if op[0] == 0][0]
+        assert order[0] == first[1] // pc
+        assert order == sorted(order) or order == sorted(order, reverse=True)
+    assert nla.panel_order("L", "L", "N", "S", 1000, 256) == [0, 1, 2, 3]
+    assert nla.panel_order("L", "U", "N", "S", 1000, 256) == [3, 2, 1, 0]
+    assert nla.panel_order("L", "L", "N", "S", 0, 256) == []
+    with pytest.raises(nla.NextLAError):
+        nla.panel_order("X", "L", "N", "S", 100, 10)

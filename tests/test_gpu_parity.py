@@ -447,3 +447,54 @@ def test_large_size_properties_low_precision(nla, gpu, dtype_name, side, uplo, t
         assert torch.equal(X3, X)
     finally:
         gpu.set_option("streams", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+@pytest.mark.parametrize("ib", [128, 256, 512, 1024, 2048])
+def test_block_inverse_leaves(nla, gpu, dtype, ib):
+    """Float32 / Float16 solves with diagonal blocks inverted up to order `inv_block` (tri_inv.cuh: FP64 128-blocks, doubling in
+    the next wider type, one triangular GEMM per block): every solve variant, ragged order, alpha != 1, both input recipes,
+    against the tolerance and against the 128-wide leaves."""
+    n, m = 1500, 200
+    try:
+        for recipe in (("scaled", "reference") if dtype == np.float32 else ("scaled",)):   # the reference recipe underflows Float16
+            for side, uplo, trans in itertools.product(SIDES, UPLOS, "NT"):
+                A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=ib + 5, recipe=recipe)
+                gpu.set_option("inv_block", ib)
+                got = run_gpu(nla, side, uplo, trans, 1.5, "S", A, B0)
+                err = rp.error_metric(side, uplo, trans, 1.5, "S", A, B0, got)
+                assert err < TOL[dtype], (recipe, side, uplo, trans, err)
+                gpu.set_option("inv_block", 128)
+                base = run_gpu(nla, side, uplo, trans, 1.5, "S", A, B0)
+                assert rel(got, base) < (2e-5 if dtype == np.float32 else 1e-2), (recipe, side, uplo, trans)
+    finally:
+        gpu.set_option("inv_block", 0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float16])
+@pytest.mark.parametrize("side,uplo,trans,func", [("L", "L", "N", "S"), ("L", "U", "N", "S"), ("R", "L", "T", "M"), ("L", "L", "T", "S")])
+def test_gated_arrival_of_A(nla, gpu, dtype, side, uplo, trans, func):
+    """nla_rectrxm_gated: A becomes valid panel by panel (here: copied on a side stream from a pristine matrix, each panel behind a
+    spin kernel so that the solve really has to wait), result identical to the plain call."""
+    import torch
+
+    n, m, pc = 2048, 384, 512
+    A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=31, recipe="scaled")
+    dA_full = nla.colmajor(A)
+    want = run_gpu(nla, side, uplo, trans, 1.25, func, A, B0)
+    dA = torch.full_like(dA_full, float("nan"))   # nothing valid until its panel has arrived
+    dB = nla.colmajor(B0)
+    order = nla.panel_order(side, uplo, trans, func, n, pc)
+    side_stream = torch.cuda.Stream()
+    events = [torch.cuda.Event() for _ in range(n // pc)]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side_stream):
+        for p in order:
+            torch.cuda._sleep(20_000_000)   # ~10 ms per panel
+            dA[:, p * pc:(p + 1) * pc].copy_(dA_full[:, p * pc:(p + 1) * pc])
+            events[p].record(side_stream)
+    nla.unified_rectrxm_gated(side, uplo, trans, 1.25, func, dA, dB, pc, events)
+    torch.cuda.synchronize()
+    got = nla.to_numpy(dB)
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, want), (side, uplo, trans, func)

@@ -76,3 +76,53 @@ def test_two_rank_gloo_sharded_solve(nla, tmp_path, side, func):
     parts = [np.load(tmp_path / f"shard{r}.npy") for r in range(world)]
     got = np.concatenate(parts, axis=1 if side == "L" else 0)
     assert np.array_equal(got, want)  # sharding RHS vectors cannot change any bit of the per-vector arithmetic
+
+
+def _panel_worker(rank, world, port, n, pc, order, out_dir):
+    import sys
+
+    import torch
+    import torch.distributed as dist
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as ge
+    from importlib import import_module
+
+    nla = ge.load_package()
+    sh = import_module(nla.__name__ + ".sharded")
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    full = torch.rand(n, n, dtype=torch.float64, generator=g)
+    A = full.clone().t() if rank == 0 else torch.zeros(n, n, dtype=torch.float64).t()   # column-major n x n
+    seen = []
+    snapshots = []
+
+    def on_panel(p):
+        seen.append(p)
+        snapshots.append(A[:, p * pc:min(n, (p + 1) * pc)].clone())
+
+    sh.broadcast_panels(A.t(), order, pc, src=0, on_panel=on_panel)
+    ok = seen == list(order) and torch.equal(A, full.t())
+    for p, snap in zip(seen, snapshots):   # a panel is complete when its callback runs (what the CUDA path records an event for)
+        ok = ok and torch.equal(snap, full.t()[:, p * pc:min(n, (p + 1) * pc)])
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_panel_broadcast(nla, tmp_path):
+    """The pipelined broadcast of A (sharded.broadcast_panels): column panels in the schedule's consumption order
+    (nla_panel_order), ragged last panel, every rank ends with the owner's matrix."""
+    import torch.multiprocessing as mp
+    from importlib import import_module
+
+    sh = import_module(nla.__name__ + ".sharded")
+    n = 200
+    pc, npan = sh.panel_geometry(n, 3, gran=8)
+    assert pc % 8 == 0 and (npan - 1) * pc < n <= npan * pc
+    order = nla.panel_order("L", "U", "N", "S", n, pc)   # backward walk: last panel first
+    assert order == list(range(npan - 1, -1, -1))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_panel_worker, args=(2, port, n, pc, order, str(tmp_path)), nprocs=2, join=True)
+    assert all(bool(np.load(tmp_path / f"ok{r}.npy")[0]) for r in range(2))

@@ -273,12 +273,9 @@ def main():
                 rc = lib.nla_rectrxm_host(h._h, b"L", b"L", b"N", b"S", 0, n, m, 1.0, hostA.data_ptr(), n, hostX.data_ptr(), n)
                 assert rc == 0, rc
             else:
-                if rank == 0:
-                    A_store.copy_(hostA, non_blocking=True)
-                dist.broadcast(A_store, src=0)
-                X.t().copy_(hostX, non_blocking=True)
-                nla.unified_rectrxm("L", "L", "N", 1.0, "S", A, X, handle=h)
-                hostX.copy_(X.t(), non_blocking=True)
+                # host A -> owner GPU -> all GPUs panel by panel; every rank streams its own B through the library's host pipeline
+                sharded.unified_rectrxm_pipelined_host("L", "L", "N", 1.0, "S", A, hostA.t() if hostA is not None else None, hostX.t(),
+                                                       src=0, panels=8, handle=h)
                 torch.cuda.synchronize()
             return time.perf_counter() - t0
 
@@ -295,7 +292,7 @@ def main():
         e2e = {"value": e2e_steps * flops_per_step_all / tt * 1e-12, "unit": UNIT,
                "h2d_bytes_per_step": (n * n + n * m * world) * es, "d2h_bytes_per_step": n * m * world * es, "steps": e2e_steps,
                "ms_per_step": tt / e2e_steps * 1e3, "api": "nla_rectrxm_host (pinned host A and B in, B out)" if world == 1 else
-               "H2D + ncclBroadcast(A) + nla_rectrxm + D2H per rank"}
+               "sharded.unified_rectrxm_pipelined_host: H2D(A panels) + ncclBroadcast per panel + nla_rectrxm_hostb_gated (B streamed in chunks, launches gated on the panels of A)"}
         # check the e2e result too
         Xh = hostX.to(dev).t()
         R = torch.tril(A) @ Xh - B0

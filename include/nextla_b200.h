@@ -67,6 +67,13 @@ int nla_rectrxm_gated(nla_handle_t handle, char side, char uplo, char trans, cha
 int64_t nla_panel_order(char side, char uplo, char trans, char func, int64_t n, int64_t panel_cols, int64_t *order,
                         int64_t max_panels);
 
+/* Host B, device A: the multi-GPU end-to-end path.  A is (becoming) resident on this device -- panel_events as in nla_rectrxm_gated,
+ * n_panels = 0 if it is already complete -- while this rank's right-hand sides live in host memory: B_host is streamed through
+ * the device exactly as in nla_rectrxm_host (chunks in first-touch order, copied back as soon as they are final).  Synchronous. */
+int nla_rectrxm_hostb_gated(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
+                            double alpha, const void *A_dev, int64_t lda, void *B_host, int64_t ldb, int64_t panel_cols,
+                            int64_t n_panels, void *const *panel_events);
+
 /* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
  * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
  * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */

@@ -1241,23 +1241,25 @@ int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t
   }
 }
 
+}  // extern "C"
+
 // Host-buffer entry point: the e2e path.  Nothing is staged wholesale: A travels as 1024x1024 tiles of the referenced
 // triangle and B as chunks of 1024 vector elements (row blocks for side 'L', column blocks for side 'R'), queued on one
 // copy-in stream in the order the schedule FIRST touches them; every op waits only for the last tile/chunk it needs, and a
 // chunk of B is copied back as soon as the last op that writes it has run.  For C2 this hides all but the first ~5 ms of
 // the 3 GiB of input and the last chunk of output behind the solve.
-int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
-                     const void* A_host, int64_t lda, void* B_host, int64_t ldb) {
-  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+// `A_dev` != nullptr: A is (or is becoming, see `gate`) resident on the device with leading dimension `lda_dev`; only B is staged.
+static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                         const void* A_host, int64_t lda, void* B_host, int64_t ldb, const void* A_dev, int64_t lda_dev, const Gate* gate) {
   Problem P;
-  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A_host, lda, B_host, ldb);
+  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A_dev ? A_dev : A_host, A_dev ? lda_dev : lda, B_host, ldb);
   if (rc != NLA_OK) return rc;
   if (n == 0 || m == 0) return NLA_OK;
   NLA_CUDA(h, cudaSetDevice(h->device));
   const size_t es = dtype_size(dtype);
   const int64_t brows = P.right ? m : n, bcols = P.right ? n : m;
-  const int64_t dlda = (n + 1) & ~1ll, dldb = (brows + 1) & ~1ll;   // compact, TMA-friendly leading dimensions on the device
-  const size_t a_bytes = (size_t)dlda * n * es, b_bytes = (size_t)dldb * bcols * es;
+  const int64_t dlda = A_dev ? lda_dev : ((n + 1) & ~1ll), dldb = (brows + 1) & ~1ll;   // compact, TMA-friendly leading dimensions on the device
+  const size_t a_bytes = A_dev ? 0 : (size_t)dlda * n * es, b_bytes = (size_t)dldb * bcols * es;
   if (h->stage_a_bytes < a_bytes) {
     if (h->stage_a) cudaFree(h->stage_a);
     h->stage_a = nullptr; h->stage_a_bytes = 0;
@@ -1275,7 +1277,7 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
   cudaStream_t s_in = h->host_streams[0], s_out = h->host_streams[1], s_cmp = h->host_streams[2];
 
   Problem D = P;   // the same problem on the device copies
-  D.A = h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
+  D.A = A_dev ? A_dev : h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
   D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
   Plan plan;
   switch (dtype) {
@@ -1320,6 +1322,7 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
     int nd = -1;
     for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
       for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
+        if (A_dev) continue;                             // A is not staged by this call
         if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
         int& ord = a_order[(size_t)(ti * nt + tj)];
         if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
@@ -1365,10 +1368,16 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
 
   // ---- compute + copy-out ----
   int waited = -1;
+  std::vector<char> gate_waited(gate ? (size_t)gate->n_panels : 0, 0);
   for (size_t oi = 0; oi < ops.size(); oi++) {
     if (need[oi] > waited) {
       NLA_CUDA(h, cudaStreamWaitEvent(s_cmp, in_ev[(size_t)need[oi]], 0));
       waited = need[oi];
+    }
+    if (gate) {
+      int64_t gc0, gc1;
+      op_columns(D, ops[oi], gc0, gc1);
+      if ((rc = gate_wait(h, gate, gate_waited, gc0, gc1, s_cmp)) != NLA_OK) return rc;
     }
     std::vector<Op> one(1, ops[oi]);
     switch (dtype) {
@@ -1392,6 +1401,25 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
   for (auto e : in_ev) cudaEventDestroy(e);
   for (auto e : out_ev) cudaEventDestroy(e);
   return NLA_OK;
+}
+
+extern "C" {
+
+int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                     const void* A_host, int64_t lda, void* B_host, int64_t ldb) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  return host_pipeline(h, side, uplo, trans, func, dtype, n, m, alpha, A_host, lda, B_host, ldb, nullptr, 0, nullptr);
+}
+
+int nla_rectrxm_hostb_gated(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
+                            const void* A_dev, int64_t lda, void* B_host, int64_t ldb, int64_t panel_cols, int64_t n_panels,
+                            void* const* panel_events) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (n > 0 && m > 0 && !A_dev) return NLA_ERR_NULL_POINTER;
+  if (n_panels < 0 || (n_panels > 0 && (panel_cols <= 0 || n_panels * panel_cols < n || !panel_events))) return NLA_ERR_INVALID_DIM;
+  for (int64_t p = 0; p < n_panels; p++) if (!panel_events[p]) return NLA_ERR_NULL_POINTER;
+  Gate gate{panel_cols, n_panels, (cudaEvent_t const*)panel_events};
+  return host_pipeline(h, side, uplo, trans, func, dtype, n, m, alpha, nullptr, 0, B_host, ldb, A_dev, lda, n_panels > 0 ? &gate : nullptr);
 }
 
 }  // extern "C"

@@ -105,3 +105,55 @@ def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float
         torch.cuda.current_stream(dev).wait_stream(bs)
         return B_local
     return unified_rectrxm_gated(side, uplo, transpose, alpha, func, A, B_local, pc, events, handle=handle)
+
+
+_host_pipe = {}
+
+
+def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: float, func: str, A_dev, A_host, B_host, src: int = 0,
+                                   group=None, panels: int = 8, handle=None):
+    """End-to-end multi-GPU call with HOST buffers.  `A_host` (pinned, column-major, significant on `src` only) goes
+    host -> owner GPU -> every GPU panel by panel (H2D copy + NCCL broadcast on a side stream, in consumption order) into
+    `A_dev` (column-major, ld = n); the rank's right-hand sides `B_host` (column-major ndarray-like torch CPU tensor, pinned)
+    are streamed through the device by the library's host pipeline (nla_rectrxm_hostb_gated: chunks of B in first-touch
+    order, every launch gated on the panels of A it reads, results copied back as soon as they are final).  Synchronous."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _ch, _check, _desc, default_handle, load_library, panel_order
+
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else src
+    n = A_dev.shape[0]
+    dev = A_dev.device
+    if dev not in _host_pipe:
+        _host_pipe[dev] = torch.cuda.Stream(device=dev)
+    bs = _host_pipe[dev]
+    bs.wait_stream(torch.cuda.current_stream(dev))
+    pc, npan = panel_geometry(n, panels)
+    order = panel_order(side, uplo, transpose, func, n, pc)
+    events = [torch.cuda.Event() for _ in range(npan)]
+    A_store = A_dev.t()
+    Ah_store = A_host.t() if rank == src else None
+    with torch.cuda.stream(bs):
+        for p in order:
+            rows = slice(p * pc, min(n, (p + 1) * pc))
+            if rank == src:   # only the referenced triangle crosses PCIe: rows [p*pc, n) of a lower panel, [0, (p+1)*pc) of an upper one
+                r0, r1 = (p * pc, n) if uplo == "L" else (0, min(n, (p + 1) * pc))
+                A_store[rows, r0:r1].copy_(Ah_store[rows, r0:r1], non_blocking=True)
+            if multi:
+                dist.broadcast(A_store[rows], src=src, group=group)
+            events[p].record(bs)
+    h = handle or default_handle(dev.index)
+    pa, ar, ac, lda, dta = _desc(A_dev)
+    if B_host.dim() != 2 or (B_host.shape[0] > 1 and B_host.stride(0) != 1):
+        raise ValueError("B_host must be a column-major 2-D CPU tensor")
+    m = B_host.shape[1] if side == "L" else B_host.shape[0]
+    ldb = B_host.stride(1) if B_host.shape[1] > 1 else max(1, B_host.shape[0])
+    evs = (ctypes.c_void_p * npan)(*[ctypes.c_void_p(e.cuda_event) for e in events])
+    rc = load_library().nla_rectrxm_hostb_gated(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda,
+                                                B_host.data_ptr(), ldb, pc, npan, evs)
+    _check(rc, h._h)
+    return B_host

@@ -340,6 +340,7 @@ def test_cta_pair_kernel(nla, gpu, dtype, cg):
 
     rng = np.random.RandomState(11)
     gpu.set_option("tc_cg", cg)
+    gpu.set_option("tc_persist", 0)   # Float16 would otherwise take the persistent pair kernel (test_persistent_pair_kernel)
     try:
         for (M, N, K) in [(256, 256, 128), (384, 520, 320), (1000, 1544, 1096), (2048, 4096, 2048)]:
             A = (rng.rand(M, K) - 0.5).astype(dtype); B = (rng.rand(K, N) - 0.5).astype(dtype); C = rng.rand(M, N).astype(dtype)
@@ -356,6 +357,7 @@ def test_cta_pair_kernel(nla, gpu, dtype, cg):
             assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (side, uplo, trans, func)
     finally:
         gpu.set_option("tc_cg", 0)
+        gpu.set_option("tc_persist", 1)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float16])
@@ -518,3 +520,38 @@ def test_pipelined_host_path_single_rank(nla, gpu, side, uplo, trans, func):
     torch.cuda.synchronize()
     got = np.asfortranarray(hB.numpy())
     assert rel(got, want) < 1e-13   # same schedule; the host pipeline cuts the large updates into 1024-wide pieces
+
+
+def test_persistent_pair_kernel(nla, gpu):
+    """The persistent CTA-pair kernel (csrc/gemm_tc3.cuh, Float16: static tile list per cluster, two TMEM accumulators, 8 drain
+    warps) against FP64 truth and against the one-tile kernels: updates with a single tile, odd tile counts, more tiles than
+    clusters (several tiles per cluster: ring and accumulator hand-over across tiles), ragged M/N/K, every majorness
+    instantiation; then every solve / multiply variant with block-inverse leaves (windows 4 / 5, `dup` epilogue), ragged order."""
+    import torch
+
+    dtype = np.float16
+    rng = np.random.RandomState(21)
+    assert gpu.get_option("tc_persist") == 1
+    for (M, N, K) in [(256, 256, 64), (384, 520, 320), (1000, 1544, 1096), (2304, 5000, 200), (4096, 8192, 1024)]:
+        A = (rng.rand(M, K) - 0.5).astype(dtype); B = (rng.rand(K, N) - 0.5).astype(dtype); C = rng.rand(M, N).astype(dtype)
+        want = C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)
+        for ta, tb in (("N", "N"), ("T", "N"), ("N", "T")):
+            Ain = np.asfortranarray(A.T.copy() if ta == "T" else A); Bin = np.asfortranarray(B.T.copy() if tb == "T" else B)
+            dA, dB = nla.colmajor(Ain), nla.colmajor(Bin)
+            dC = nla.colmajor(np.asfortranarray(C))
+            nla._gemm(dC, dA, dB, -1, transa=ta, transb=tb); torch.cuda.synchronize()
+            got = nla.to_numpy(dC)
+            assert rel(got, want) < 1e-3, (M, N, K, ta, tb)
+            gpu.set_option("tc_persist", 0)
+            try:
+                dC2 = nla.colmajor(np.asfortranarray(C))
+                nla._gemm(dC2, dA, dB, -1, transa=ta, transb=tb); torch.cuda.synchronize()
+            finally:
+                gpu.set_option("tc_persist", 1)
+            assert rel(got, nla.to_numpy(dC2)) < 1e-3, (M, N, K, ta, tb)
+    for n, m in ((1500, 520), (2048, 1024), (3000, 300)):
+        for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=n + 1, recipe="scaled")
+            got = run_gpu(nla, side, uplo, trans, 1.5, func, A, B0)
+            assert np.isfinite(got).all()
+            assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (n, m, side, uplo, trans, func)

@@ -344,6 +344,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int rseg = (lane % LPC) * VEC;
         const int grow = tm * TC_BM + quarter * 32 + rseg;
         uint4 oldv[PASSES];
+#pragma unroll
+        for (int ps = 0; ps < PASSES; ps++) oldv[ps] = make_uint4(0u, 0u, 0u, 0u);
         if (need_old) {
 #pragma unroll
           for (int ps = 0; ps < PASSES; ps++) {
@@ -370,11 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int e = 0; e < VEC; e += 4) *reinterpret_cast<float4*>(&accv[e]) = *reinterpret_cast<const float4*>(&stg[cl * 32 + rseg + e]);
 #pragma unroll
             for (int e = 0; e < VEC; e++) {
-              float v = need_old ? tc_to_float<T>(ov[e]) : 0.f;
-              if (beta != 1.0f) v = tc_to_float<T>(tc_from_float<T>(beta * v));
+              // branch-free: for beta = 1 / post = 1 the extra roundings are exact no-ops, and a branchy version is cloned by the
+              // compiler for every combination (instruction-cache pressure in the drain, see gemm_tc3.cuh); oldv is zero when unused
+              float v = tc_to_float<T>(tc_from_float<T>(beta * tc_to_float<T>(ov[e])));
               v += p.sgn * accv[e];
-              if (post != 1.0f) v = post * tc_to_float<T>(tc_from_float<T>(v));
-              outv[e] = tc_from_float<T>(v);
+              outv[e] = tc_from_float<T>(post * tc_to_float<T>(tc_from_float<T>(v)));
             }
             T* dst = cbase + grow + (long long)(tn * BN + col) * p.ldc;
             if (grow + VEC <= p.M) {

@@ -2,7 +2,7 @@
 //
 // Same operation, operands, TMA maps and epilogue arithmetic as gemm_tc.cuh / gemm_tc2.cuh (C <- post*(beta*C + sgn*opA(A)*opB(B)),
 // src/matmul.jl:5-81 in the reference).  What changes is the life cycle of a CTA.  ncu on the one-tile-per-CTA kernels for the
-// mid-size launches of a solve (profiles/r01_ncu_f16_mid_leaf_summary.csv: M = K = 1024 update 59 us, block-inverse leaf 44 us)
+// mid-size launches of a solve (profiles/r01_ncu_f16_mid_onetile_summary.csv, r01_ncu_f16_leaf_onetile_summary.csv: M = K = 1024 update 59 us, block-inverse leaf 44 us)
 // shows tensor pipe 21-27 % active with DRAM at 10-18 % and L2 at 17-28 %: nothing is saturated, the time goes into per-tile
 // fixed costs (barrier/TMEM set-up, an empty operand ring at the start of every tile, a latency-bound drain of 4 warps while the
 // tensor core idles).  Here one pair of CTAs per TPC stays resident and walks a static list of 256 x 256 tiles:

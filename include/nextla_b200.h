@@ -21,7 +21,7 @@ enum nla_dtype { NLA_F64 = 0, NLA_F32 = 1, NLA_F16 = 2 }; /* Float64 / Float32 /
 
 enum nla_status {
   NLA_OK = 0,
-  NLA_ERR_INVALID_CHAR = 1,   /* side/uplo/trans/func not in the documented set (the reference silently coerces, src/rectrxm.jl:105-123) */
+  NLA_ERR_INVALID_CHAR = 1,   /* side/uplo/trans/diag/func not in the documented set (the reference silently coerces, src/rectrxm.jl:105-123) */
   NLA_ERR_INVALID_DIM = 2,    /* negative n/m or leading dimension too small */
   NLA_ERR_INVALID_DTYPE = 3,
   NLA_ERR_NULL_POINTER = 4,
@@ -47,6 +47,13 @@ int nla_version(void);
  * m = number of independent right-hand-side vectors.  'C' == 'T' for the real element types supported. */
 int nla_rectrxm(nla_handle_t handle, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m,
                 double alpha, const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
+
+/* BLAS-style entry with the `diag` flag: trsm(side, uplo, transa, diag, A, B, alpha) / trmm(...)   -- src/trsm.jl:186-205, src/trmm.jl:430-448
+ * (SURVEY.md 8(f1)).  The reference's wrappers accept `transa` and `diag` and ignore both (and do not recurse: n <= 1024 / 16); here
+ * `trans` is honoured, the recursion is the one of nla_rectrxm, and diag = 'U' treats the diagonal of A as ones without reading it
+ * (what the unit-lower solve of a recursive LU needs, src/lu.jl:277).  diag = 'N' is exactly nla_rectrxm. */
+int nla_trxm(nla_handle_t handle, char side, char uplo, char trans, char diag, char func, int dtype, int64_t n, int64_t m,
+             double alpha, const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
 
 /* Same operation with HOST buffers (pinned or pageable): stages A once and streams B through the device in
  * RHS slabs, overlapping copies with compute; synchronous (returns when B_host holds the result).

@@ -53,6 +53,7 @@ def load_library():
         "nla_last_cuda_error": (I, [H]),
         "nla_version": (I, []),
         "nla_rectrxm": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
+        "nla_trxm": (I, [H, CH, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
         "nla_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L]),
         "nla_rectrxm_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P, L, L, c.POINTER(c.c_void_p)]),
         "nla_rectrxm_hostb_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, L, L, c.POINTER(c.c_void_p)]),
@@ -76,7 +77,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order",
+            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 
@@ -305,19 +306,32 @@ def GEMM_SUB(A, B, C, **kw):
     return _gemm(A, B, C, -1, **kw)
 
 
+def unified_trxm(side: str, uplo: str, transpose: str, diag: str, alpha: float, func: str, A, B, stream=None, handle: Optional[Handle] = None):
+    """unified_rectrxm with the BLAS `diag` flag (nla_trxm): diag = 'U' treats the diagonal of A as ones without reading it."""
+    h = handle or default_handle(A.device.index)
+    pa, ar, ac, lda, dta = _desc(A)
+    pb, br, bc, ldb, dtb = _desc(B)
+    if dta != dtb or ar != ac:
+        raise NextLAError("A must be square and share B's element type")
+    n = ar
+    m = bc if side == "L" else br
+    if (side == "L" and br != n) or (side == "R" and bc != n):
+        raise NextLAError("dimension mismatch between A and B")
+    rc = load_library().nla_trxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(diag), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
+                                 _stream_ptr(stream))
+    _check(rc, h._h)
+    return B
+
+
 def trsm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
-    """trsm(side, uplo, transa, diag, A, B, alpha) -- src/trsm.jl:186-205.  Unlike the reference (which ignores
-    `transa` and is limited to one leaf) this honours `transa` and recurses; `diag` must be 'N'."""
-    if diag != "N":
-        raise NextLAError("unit-diagonal solves are not implemented (the reference ignores diag, src/trsm.jl:186)")
-    return unified_rectrxm(side, uplo, transa, alpha, "S", A, B, **kw)
+    """trsm(side, uplo, transa, diag, A, B, alpha) -- src/trsm.jl:186-205.  Unlike the reference (which ignores `transa` and `diag`
+    and is limited to one leaf) this honours both and recurses."""
+    return unified_trxm(side, uplo, transa, diag, alpha, "S", A, B, **kw)
 
 
 def trmm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
     """trmm(side, uplo, transa, diag, A, B, alpha) -- src/trmm.jl:430-448."""
-    if diag != "N":
-        raise NextLAError("unit-diagonal products are not implemented (the reference ignores diag, src/trmm.jl:430)")
-    return unified_rectrxm(side, uplo, transa, alpha, "M", A, B, **kw)
+    return unified_trxm(side, uplo, transa, diag, alpha, "M", A, B, **kw)
 
 
 def plan(side: str, uplo: str, transpose: str, func: str, n: int, leaf: int = 0):

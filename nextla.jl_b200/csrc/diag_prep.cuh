@@ -36,6 +36,7 @@ struct DiagPrepParams {
   const T* A; long long t_rs, t_cs;   // Teff(r,k) = A[r*t_rs + k*t_cs]
   int n;                              // order of Teff
   int lower, solve;
+  int unit;                           // 1: unit diagonal (stored diagonal not read)
   int block0;                         // first diagonal block handled by this launch (block b = blockIdx.x + block0)
   TO* W;                              // K-major workspace, 128 x 128 per block
   int pitch, ib;                      // elements between consecutive rows of W; order of the enclosing inverse block (128: none)
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(DP_THREADS) diag_prep_kernel(const DiagPrepPar
     float v = 0.f;
     if (r < t && k < t) {
       const int R = p.lower ? r : t - 1 - r, K = p.lower ? k : t - 1 - k;
-      if (k <= r) v = (float)Traits<T>::ld(Ab + (long long)R * p.t_rs + (long long)K * p.t_cs);
+      if (k <= r) v = (p.unit && k == r) ? 1.f : (float)Traits<T>::ld(Ab + (long long)R * p.t_rs + (long long)K * p.t_cs);
     } else if (r == k) {
       v = 1.f;   // identity padding keeps the substitution finite; padded entries are written as zeros below
     }

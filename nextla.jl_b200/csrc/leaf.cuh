@@ -27,6 +27,8 @@ template <typename T>
 struct LeafParams {
   const T* A; long long a_rs, a_cs;  // Teff(r,k) = A[r*a_rs + k*a_cs] (block origin; already "transposed" by strides)
   int lower;                         // 1: Teff lower triangular, 0: upper
+  int unit;                          // 1: unit diagonal -- the stored diagonal is not read (BLAS diag = 'U'; the reference's trsm/trmm
+                                     // wrappers accept the flag and ignore it, src/trsm.jl:186, src/trmm.jl:430)
   int t;                             // block order
   T* V; long long es, vs;            // vector v, element e at V[e*es + v*vs]
   long long m;                       // number of vectors
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(LEAF_W) leaf_kernel(const LeafParams<T> p) {
   // ---- stage the triangular tile (normalised to lower/forward by index reversal for upper) ----
   for (int r = tid; r < tp; r += LEAF_W) {
     Acc d = Acc(1);
-    if (r < t) {
+    if (r < t && !p.unit) {
       const int R = p.lower ? r : t - 1 - r;
       d = Traits<T>::ld(p.A + (long long)R * (p.a_rs + p.a_cs));
     }
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(LEAF_W) leaf_kernel(const LeafParams<T> p) {
       const bool inside = SOLVE ? (k < r) : (k <= r);
       if (inside && r < t) {
         const int R = p.lower ? r : t - 1 - r, K = p.lower ? k : t - 1 - k;
-        v = Traits<T>::ld(p.A + (long long)R * p.a_rs + (long long)K * p.a_cs);
+        v = (p.unit && k == r) ? Acc(1) : Traits<T>::ld(p.A + (long long)R * p.a_rs + (long long)K * p.a_cs);
         if (SOLVE) v = v / dv[r];   // the reference divides every entry by its row's diagonal (src/trsm.jl:24)
       }
       Lb[e] = v;

@@ -91,6 +91,7 @@ static inline size_t dtype_size(int dtype) { return dtype == NLA_F64 ? 8 : dtype
 struct Problem {
   int dtype;
   bool solve, right;
+  bool unit;         // unit diagonal: the stored diagonal of A is not referenced
   bool teff_trans;   // Teff(r,k) = A[k,r] instead of A[r,k]
   bool lower;        // Teff lower triangular
   int64_t n, m;
@@ -162,7 +163,7 @@ static int launch_leaf(nla_context* ctx, const Problem& P, const Op& o, int64_t 
   lp.A = A;
   lp.a_rs = P.teff_trans ? P.lda : 1;
   lp.a_cs = P.teff_trans ? 1 : P.lda;
-  lp.lower = P.lower; lp.t = (int)o.sz;
+  lp.lower = P.lower; lp.t = (int)o.sz; lp.unit = P.unit;
   lp.V = (T*)P.B + o.off * P.es + v0 * P.vs;
   lp.es = P.es; lp.vs = P.vs; lp.m = nv;
   lp.pre = o.pre; lp.post = o.post;
@@ -400,7 +401,7 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
 
 template <typename T, typename TO = T>
 static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t t_cs, int64_t n, bool lower, bool solve, int64_t block0,
-                            int64_t nblocks, TO* W, cudaStream_t st, int64_t ib = DP_B) {
+                            int64_t nblocks, TO* W, cudaStream_t st, int64_t ib = DP_B, bool unit = false) {
   static bool configured[64] = {false};
   if (!configured[ctx->device & 63]) {
     NLA_CUDA(ctx, (cudaFuncSetAttribute(diag_prep_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES)));
@@ -408,7 +409,7 @@ static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t 
   }
   DiagPrepParams<T, TO> dp;
   dp.A = A; dp.t_rs = t_rs; dp.t_cs = t_cs; dp.n = (int)n; dp.lower = lower; dp.solve = solve; dp.block0 = (int)block0; dp.W = W;
-  dp.pitch = (int)ib; dp.ib = (int)ib;
+  dp.pitch = (int)ib; dp.ib = (int)ib; dp.unit = unit;
   diag_prep_kernel<T, TO><<<(unsigned)nblocks, DP_THREADS, DP_SMEM_BYTES, st>>>(dp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
@@ -519,7 +520,7 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
   sp.T = (int)o.sz; sp.off = (int)o.off; sp.v_base = (int)v0; sp.v_count = (int)nv;
   sp.A = (const double*)P.A;
   sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
-  sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = o.pre; sp.post = o.post;
+  sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = o.pre; sp.post = o.post; sp.unit = P.unit;
   const int v = (P.teff_trans ? 4 : 0) | (P.lower ? 2 : 0) | (P.solve ? 1 : 0);
   switch (v) {
     case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
@@ -540,7 +541,7 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
                           bool copied = false) {
   if (maps.prep_per_leaf) {
     const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
-    int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, o.off / DP_B, 1, (T*)ctx->diag_ws, st);
+    int rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, o.off / DP_B, 1, (T*)ctx->diag_ws, st, DP_B, P.unit);
     if (rc != NLA_OK) return rc;
   }
   GemmTcParams gp{};
@@ -853,7 +854,7 @@ static int prepare_block_inverses(nla_context* ctx, const Problem& P, int64_t ib
   const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
   const int64_t r0 = blk0 * ib, r1 = std::min(nblocks * DP_B, blk1 * ib);   // workspace rows of this range
   if (r1 <= r0) return NLA_OK;
-  int rc = launch_diag_prep<T, Acc>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, true, r0 / DP_B, (r1 - r0) / DP_B, (Acc*)ctx->inv_acc, st, ib);
+  int rc = launch_diag_prep<T, Acc>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, true, r0 / DP_B, (r1 - r0) / DP_B, (Acc*)ctx->inv_acc, st, ib, P.unit);
   if (rc != NLA_OK) return rc;
   TriInvParams<T, Acc> tp;
   tp.A = (const T*)P.A; tp.t_rs = t_rs; tp.t_cs = t_cs; tp.n = (int)P.n; tp.ib = (int)ib; tp.lower = P.lower;
@@ -911,7 +912,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
         } else {
           rc = prepare_block_inverses<T>(ctx, P, maps.ib, stream, 0, nb);
         }
-      } else rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream);
+      } else rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream, DP_B, P.unit);
       if (rc != NLA_OK) return rc;
       if (!P.solve && ctx->trmm_batched) return trmm_batched_tc<T>(ctx, P, maps, stream);
     }
@@ -947,7 +948,9 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
 static inline bool valid(nla_handle_t h) { return h && h->magic == NLA_MAGIC; }
 
 static int make_problem(Problem& P, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
-                        const void* A, int64_t lda, void* B, int64_t ldb) {
+                        const void* A, int64_t lda, void* B, int64_t ldb, char diag = 'N') {
+  if (diag != 'N' && diag != 'U') return NLA_ERR_INVALID_CHAR;
+  P.unit = diag == 'U';
   if ((side != 'L' && side != 'R') || (uplo != 'L' && uplo != 'U') || (trans != 'N' && trans != 'T' && trans != 'C') ||
       (func != 'S' && func != 'M'))
     return NLA_ERR_INVALID_CHAR;
@@ -1188,6 +1191,17 @@ int64_t nla_panel_order(char side, char uplo, char trans, char func, int64_t n, 
     }
   }
   return cnt;
+}
+
+int nla_trxm(nla_handle_t h, char side, char uplo, char trans, char diag, char func, int dtype, int64_t n, int64_t m, double alpha,
+             const void* A, int64_t lda, void* B, int64_t ldb, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A, lda, B, ldb, diag);
+  if (rc != NLA_OK) return rc;
+  if (n == 0 || m == 0) return NLA_OK;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  return dispatch(h, P, (cudaStream_t)stream);
 }
 
 static int leaf_entry(nla_handle_t h, bool solve, char side, char uplo, int dtype, int64_t n, int64_t m, const void* A, int64_t lda,

@@ -38,6 +38,7 @@ struct SlabParams {
   double* B;              // column-major, vectors are columns
   long long ldb;
   double beta, post;
+  int unit;               // 1: unit diagonal (the stored diagonal is not used)
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -172,6 +173,7 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
               for (int x = 0; x < 8; x++) {
                 const int row = (h * 8 + x) * 8 + (int)g;
                 if (LOWER ? (row < kk) : (row > kk)) a[x] = 0.0;
+                if (p.unit && row == kk) a[x] = 1.0;
               }
             }
 #pragma unroll
@@ -234,7 +236,7 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
           }
           double d = 1.0;
 #pragma unroll
-          for (int pp = 0; pp < 8; pp++) if (pp == (int)g && valid) d = lrow[pp];
+          for (int pp = 0; pp < 8; pp++) if (pp == (int)g && valid && !p.unit) d = lrow[pp];
           // the reference scales every entry of a row by its diagonal (src/trsm.jl:15-18,24); one reciprocal per row
           // instead of 12 divisions keeps the FP64 pipe for the DMMAs (costs <= 1 ulp per scaled entry)
           const double rd = 1.0 / d;

@@ -91,4 +91,47 @@ end
 NextLA.GEMM_ADD!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, C::StridedCuMatrix{T}; kwargs...) where {T<:B200Float} = gemm_update!(C, A, B, 1)
 NextLA.GEMM_SUB!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, C::StridedCuMatrix{T}) where {T<:B200Float} = gemm_update!(A, B, C, -1)
 
+# trsm / trmm (src/trsm.jl:186-205, src/trmm.jl:430-448; un-exported in the reference): same argument order.  The reference ignores
+# `transa` and `diag` and runs one leaf; here both are honoured and the call recurses (nla_trxm).
+for (fname, func) in ((:trsm, 'S'), (:trmm, 'M'))
+    @eval function NextLA.$fname(side::Char, uplo::Char, transa::Char, diag::Char, A::StridedCuMatrix{T}, B::StridedCuMatrix{T},
+                                 alpha::Number = one(T)) where {T<:B200Float}
+        n = size(A, 1)
+        m = side == 'L' ? size(B, 2) : size(B, 1)
+        GC.@preserve A B check(ccall((:nla_trxm, libnextla), Cint,
+            (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
+            handle(), side, uplo, transa, diag, $func, dtype_code(T), n, m, Float64(alpha),
+            pointer(A), max(1, stride(A, 2)), pointer(B), max(1, stride(B, 2)), CUDA.stream().handle))
+        return B
+    end
+end
+
+"""
+    unified_rectrxm_gated!(side, uplo, transpose, alpha, func, A, B, panel_cols, events)
+
+Multi-GPU variant (no reference counterpart): `A` is still arriving in column panels of `panel_cols` columns (NCCL broadcast from its
+owner on a side stream, in the order `panel_order` returns); `events[p+1]` is a `CuEvent` recorded after panel `p`.  The schedule waits
+for a panel right before the first launch that reads it.
+"""
+function unified_rectrxm_gated!(side::Char, uplo::Char, transpose::Char, alpha::Number, func::Char, A::StridedCuMatrix{T},
+                                B::StridedCuMatrix{T}, panel_cols::Integer, events::Vector{CuEvent}) where {T<:B200Float}
+    n = size(A, 1)
+    m = side == 'L' ? size(B, 2) : size(B, 1)
+    hs = Ptr{Cvoid}[Base.unsafe_convert(Ptr{Cvoid}, e.handle) for e in events]
+    GC.@preserve A B events hs check(ccall((:nla_rectrxm_gated, libnextla), Cint,
+        (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Ptr{Cvoid}}),
+        handle(), side, uplo, transpose, func, dtype_code(T), n, m, Float64(alpha), pointer(A), max(1, stride(A, 2)),
+        pointer(B), max(1, stride(B, 2)), CUDA.stream().handle, Int64(panel_cols), Int64(length(events)), hs))
+    return B
+end
+
+function panel_order(side::Char, uplo::Char, transpose::Char, func::Char, n::Integer, panel_cols::Integer)
+    np = cld(n, panel_cols)
+    order = Vector{Int64}(undef, np)
+    cnt = ccall((:nla_panel_order, libnextla), Int64, (Cchar, Cchar, Cchar, Cchar, Int64, Int64, Ptr{Int64}, Int64),
+                side, uplo, transpose, func, n, panel_cols, order, np)
+    cnt < 0 && check(Cint(-cnt))
+    return order   # 0-based panel indices in consumption order
+end
+
 end # module

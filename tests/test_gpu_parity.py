@@ -555,3 +555,35 @@ def test_persistent_pair_kernel(nla, gpu):
             got = run_gpu(nla, side, uplo, trans, 1.5, func, A, B0)
             assert np.isfinite(got).all()
             assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (n, m, side, uplo, trans, func)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.float16])
+def test_unit_diagonal_trsm_trmm(nla, gpu, dtype):
+    """trsm / trmm with diag = 'U' (the reference's wrappers accept the flag and ignore it, src/trsm.jl:186): the
+    stored diagonal must not be read (it holds NaN here), and the result must equal the non-unit routine applied to the same
+    matrix with an explicit unit diagonal, and OpenBLAS with diag = 'U' -- every side/uplo/trans, leaf, fused-slab / block-inverse
+    and recursive sizes, alpha != 1."""
+    from scipy.linalg import blas
+
+    tol = {np.float64: 1e-13, np.float32: 1e-5, np.float16: 1e-2}[dtype]
+    for n, m in ((96, 40), (640, 136), (2304, 264)):
+        for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=n + 7, recipe="scaled")
+            A1 = A.copy(); np.fill_diagonal(A1, 1)
+            An = A.copy(); np.fill_diagonal(An, np.nan)
+            dA, dB = nla.colmajor(An), nla.colmajor(B0)
+            f = nla.trsm if func == "S" else nla.trmm
+            f(side, uplo, trans, "U", dA, dB, -1.5)
+            import torch
+            torch.cuda.synchronize()
+            got = nla.to_numpy(dB)
+            assert np.isfinite(got).all(), (n, side, uplo, trans, func)
+            assert rp.error_metric(side, uplo, trans, -1.5, func, A1, B0, got) < tol, (n, side, uplo, trans, func)
+            want = run_gpu(nla, side, uplo, trans, -1.5, func, A1, B0)   # non-unit path on the explicit unit diagonal
+            assert rel(got, want) < (1e-13 if dtype == np.float64 else tol), (n, side, uplo, trans, func)
+            if dtype == np.float64:
+                bf = blas.dtrsm if func == "S" else blas.dtrmm
+                ref = bf(-1.5, A, B0, side=0 if side == "L" else 1, lower=1 if uplo == "L" else 0, trans_a=0 if trans == "N" else 1, diag=1)
+                assert rel(got, ref) < 1e-13, (n, side, uplo, trans, func)
+    with pytest.raises(nla.NextLAError):
+        nla.trsm("L", "L", "N", "X", nla.colmajor(np.eye(4)), nla.colmajor(np.ones((4, 2))))

@@ -57,6 +57,7 @@ def load_library():
         "nla_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L]),
         "nla_rectrxm_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P, L, L, c.POINTER(c.c_void_p)]),
         "nla_rectrxm_hostb_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, L, L, c.POINTER(c.c_void_p)]),
+        "nla_memcpy2d_async": (I, [H, P, L, P, L, L, L, I, P]),
         "nla_panel_order": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
         "nla_trsm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
         "nla_trmm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
@@ -77,7 +78,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm",
+            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 

@@ -1465,6 +1465,18 @@ int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func
   return host_pipeline(h, side, uplo, trans, func, dtype, n, m, alpha, A_host, lda, B_host, ldb, nullptr, 0, nullptr);
 }
 
+int nla_memcpy2d_async(nla_handle_t h, void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes, int64_t width_bytes,
+                       int64_t height, int to_device, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (width_bytes < 0 || height < 0 || dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return NLA_ERR_INVALID_DIM;
+  if (width_bytes == 0 || height == 0) return NLA_OK;
+  if (!dst || !src) return NLA_ERR_NULL_POINTER;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height,
+                                to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return NLA_OK;
+}
+
 int nla_rectrxm_hostb_gated(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                             const void* A_dev, int64_t lda, void* B_host, int64_t ldb, int64_t panel_cols, int64_t n_panels,
                             void* const* panel_events) {

@@ -137,16 +137,23 @@ def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: 
     events = [torch.cuda.Event() for _ in range(npan)]
     A_store = A_dev.t()
     Ah_store = A_host.t() if rank == src else None
+    h = handle or default_handle(dev.index)
     with torch.cuda.stream(bs):
         for p in order:
             rows = slice(p * pc, min(n, (p + 1) * pc))
             if rank == src:   # only the referenced triangle crosses PCIe: rows [p*pc, n) of a lower panel, [0, (p+1)*pc) of an upper one
+                # (a pitched cudaMemcpy2DAsync: torch's copy_ of a non-contiguous host slice goes through a pageable staging copy
+                #  and blocks -- measured 600 ms per step at 4 GPUs)
                 r0, r1 = (p * pc, n) if uplo == "L" else (0, min(n, (p + 1) * pc))
-                A_store[rows, r0:r1].copy_(Ah_store[rows, r0:r1], non_blocking=True)
+                c0, c1 = rows.start, rows.stop
+                es = A_dev.element_size()
+                rc = load_library().nla_memcpy2d_async(h._h, A_store.data_ptr() + (c0 * n + r0) * es, n * es,
+                                                       Ah_store.data_ptr() + (c0 * Ah_store.stride(0) + r0) * es, Ah_store.stride(0) * es,
+                                                       (r1 - r0) * es, c1 - c0, 1, ctypes.c_void_p(bs.cuda_stream))
+                _check(rc, h._h)
             if multi:
                 dist.broadcast(A_store[rows], src=src, group=group)
             events[p].record(bs)
-    h = handle or default_handle(dev.index)
     pa, ar, ac, lda, dta = _desc(A_dev)
     if B_host.dim() != 2 or (B_host.shape[0] > 1 and B_host.stride(0) != 1):
         raise ValueError("B_host must be a column-major 2-D CPU tensor")

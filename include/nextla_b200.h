@@ -86,6 +86,14 @@ int nla_rectrxm_hostb_gated(nla_handle_t handle, char side, char uplo, char tran
 int nla_memcpy2d_async(nla_handle_t handle, void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                        int64_t width_bytes, int64_t height, int to_device, void *stream);
 
+/* laswp(A, first, last, ipiv, incx)                                                   -- src/lu.jl:470-530
+ * Row interchanges on a device matrix (rows x ncols, column-major): for i = k1..k2 (incx = 1) or k2..k1 (incx = -1) swap rows i and
+ * ipiv[i] (1-based, like the reference; ipiv is a DEVICE vector of int64 = Julia Int, entries outside [k1, k2] are not read).  With
+ * nla_trxm(..., diag = 'U') and nla_gemm_update this runs the laswp + TRSM + GEMM steps of the reference's recursive LU
+ * (getrf2!, src/lu.jl:274-280, :297) on the device; the panel factorisation stays with the caller. */
+int nla_laswp(nla_handle_t handle, int dtype, int64_t rows, int64_t ncols, void *A, int64_t lda, int64_t k1, int64_t k2,
+              const int64_t *ipiv, int incx, void *stream);
+
 /* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
  * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
  * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */

@@ -10,6 +10,7 @@ Function names and argument order follow the reference:
   LeftLowerTRMM(A, B) ... RightUpperTRMM(A, B)                 <- src/trmm.jl:332-389
   GEMM_ADD(A, B, C)  (C += A*B),  GEMM_SUB(A, B, C)  (A -= B*C) <- src/matmul.jl:69-81
   trsm(side, uplo, transa, diag, A, B, alpha), trmm(...)       <- src/trsm.jl:186-205, src/trmm.jl:430-448
+  laswp(A, first, last, ipiv, incx), getrf2_update(A, n1, ipiv) <- src/lu.jl:470-530, :274-280 (the device steps of the recursive LU)
 
 Matrices are column-major device arrays: 2-D torch CUDA tensors with stride (1, ld) (use `colmajor()` /
 `to_numpy()`).  Everything runs on the GPU through the library; there is NO CPU fallback -- importing is fine
@@ -58,6 +59,7 @@ def load_library():
         "nla_rectrxm_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P, L, L, c.POINTER(c.c_void_p)]),
         "nla_rectrxm_hostb_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, L, L, c.POINTER(c.c_void_p)]),
         "nla_memcpy2d_async": (I, [H, P, L, P, L, L, L, I, P]),
+        "nla_laswp": (I, [H, I, L, L, P, L, L, L, P, I, P]),
         "nla_panel_order": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
         "nla_trsm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
         "nla_trmm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
@@ -78,7 +80,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async",
+            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 
@@ -333,6 +335,32 @@ def trsm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
 def trmm(side, uplo, transa, diag, A, B, alpha=1.0, **kw):
     """trmm(side, uplo, transa, diag, A, B, alpha) -- src/trmm.jl:430-448."""
     return unified_trxm(side, uplo, transa, diag, alpha, "M", A, B, **kw)
+
+
+def laswp(A, first: int, last: int, ipiv, incx: int = 1, stream=None, handle: Optional[Handle] = None):
+    """laswp(A, first, last, ipiv, incx) -- src/lu.jl:470-530 on a device matrix: swap rows i and ipiv[i] (1-based) for i = first..last.
+    `ipiv` is a CUDA int64 vector."""
+    import torch
+
+    h = handle or default_handle(A.device.index)
+    pa, rows, cols, lda, dta = _desc(A)
+    if not (ipiv.is_cuda and ipiv.dtype == torch.int64 and ipiv.is_contiguous()):
+        raise NextLAError("ipiv must be a contiguous CUDA int64 vector")
+    if last > ipiv.numel():
+        raise NextLAError("ipiv is shorter than `last`")
+    _check(load_library().nla_laswp(h._h, dta, rows, cols, pa, lda, int(first), int(last), ipiv.data_ptr(), int(incx), _stream_ptr(stream)), h._h)
+    return A
+
+
+def getrf2_update(A, n1: int, ipiv, **kw):
+    """The device steps of one level of the reference's recursive LU (getrf2!, src/lu.jl:274-280) after the left panel
+    A[:, :n1] has been factored with pivots ipiv[:n1]:  laswp on the right part, A12 <- L11^-1 A12 (unit lower), A22 <- A22 - A21 A12."""
+    m, n = A.shape
+    laswp(A[:, n1:], 1, n1, ipiv, 1, **kw)                              # src/lu.jl:274
+    trsm("L", "L", "N", "U", A[:n1, :n1], A[:n1, n1:], 1.0, **kw)        # src/lu.jl:277
+    if m > n1:
+        GEMM_SUB(A[n1:, n1:], A[n1:, :n1], A[:n1, n1:], **kw)            # src/lu.jl:280
+    return A
 
 
 def plan(side: str, uplo: str, transpose: str, func: str, n: int, leaf: int = 0):

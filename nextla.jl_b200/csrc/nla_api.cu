@@ -17,6 +17,7 @@
 #include "gemm_tc3.cuh"
 #include "diag_prep.cuh"
 #include "tri_inv.cuh"
+#include "laswp.cuh"
 
 using namespace nla;
 
@@ -1474,6 +1475,28 @@ int nla_memcpy2d_async(nla_handle_t h, void* dst, int64_t dst_pitch_bytes, const
   NLA_CUDA(h, cudaSetDevice(h->device));
   NLA_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height,
                                 to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return NLA_OK;
+}
+
+int nla_laswp(nla_handle_t h, int dtype, int64_t rows, int64_t ncols, void* A, int64_t lda, int64_t k1, int64_t k2, const int64_t* ipiv,
+              int incx, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (dtype != NLA_F64 && dtype != NLA_F32 && dtype != NLA_F16) return NLA_ERR_INVALID_DTYPE;
+  if (rows < 0 || ncols < 0 || lda < std::max<int64_t>(1, rows) || (incx != 1 && incx != -1)) return NLA_ERR_INVALID_DIM;
+  if (ncols == 0 || k2 < k1) return NLA_OK;
+  if (k1 < 1 || k2 > rows) return NLA_ERR_INVALID_DIM;
+  if (!A || !ipiv) return NLA_ERR_NULL_POINTER;
+  NLA_CUDA(h, cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((ncols + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* piv = (const long long*)ipiv;
+  switch (dtype) {
+    case NLA_F64: laswp_kernel<double><<<grid, 256, 0, st>>>((double*)A, lda, ncols, k1, k2, piv, incx < 0); break;
+    case NLA_F32: laswp_kernel<float><<<grid, 256, 0, st>>>((float*)A, lda, ncols, k1, k2, piv, incx < 0); break;
+    default: laswp_kernel<__half><<<grid, 256, 0, st>>>((__half*)A, lda, ncols, k1, k2, piv, incx < 0); break;
+  }
+  h->launches++;
+  NLA_CUDA(h, cudaGetLastError());
   return NLA_OK;
 }
 

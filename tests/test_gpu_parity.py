@@ -587,3 +587,47 @@ def test_unit_diagonal_trsm_trmm(nla, gpu, dtype):
                 assert rel(got, ref) < 1e-13, (n, side, uplo, trans, func)
     with pytest.raises(nla.NextLAError):
         nla.trsm("L", "L", "N", "X", nla.colmajor(np.eye(4)), nla.colmajor(np.ones((4, 2))))
+
+
+@pytest.mark.parametrize("m,n", [(1024, 1024), (1500, 900), (700, 1100)])
+def test_recursive_lu_device_steps(nla, gpu, m, n):
+    """the reference's recursive LU (getrf2!, src/lu.jl:185-299) with its laswp + TRSM('L','L','N','U') + GEMM steps
+    (:274-280, :297) on the device (nla_laswp, nla_trxm diag = 'U', nla_gemm_update); only the <= 64-column panels are factored on the
+    host (LAPACK getrf through SciPy).  Checks P*A = L*U against the original matrix and the pivots against LAPACK's."""
+    import torch
+    from scipy.linalg import lu_factor
+
+    rng = np.random.RandomState(m + n)
+    A0 = rng.rand(m, n) - 0.5
+    dA = nla.colmajor(A0)
+    k = min(m, n)
+    ipiv = torch.zeros(k, dtype=torch.int64, device="cuda")
+
+    def getrf2(Av, pv):
+        mm, nn = Av.shape
+        if nn <= 64 or mm <= 64:
+            lu, piv = lu_factor(nla.to_numpy(Av), check_finite=False)
+            Av.copy_(torch.from_numpy(np.ascontiguousarray(lu)).cuda())
+            pv.copy_(torch.from_numpy(piv[:min(mm, nn)].astype(np.int64) + 1).cuda())   # 1-based like the reference
+            return
+        n1 = min(mm, nn) // 2                                    # src/lu.jl:255
+        getrf2(Av[:, :n1], pv[:n1])                              # :264
+        nla.getrf2_update(Av, n1, pv)                            # :274-280 on the device
+        getrf2(Av[n1:, n1:], pv[n1:min(mm, nn)])                 # :284
+        pv[n1:min(mm, nn)] += n1                                 # :291-293
+        nla.laswp(Av[:, :n1], n1 + 1, min(mm, nn), pv, 1)        # :297
+
+    getrf2(dA, ipiv)
+    torch.cuda.synchronize()
+    LU = nla.to_numpy(dA)
+    piv = ipiv.cpu().numpy() - 1
+    L = np.tril(LU[:, :k], -1) + np.eye(m, k)
+    U = np.triu(LU[:k, :])
+    PA = A0.copy()
+    for i, p in enumerate(piv):
+        if p != i:
+            PA[[i, p]] = PA[[p, i]]
+    assert np.linalg.norm(PA - L @ U) / np.linalg.norm(A0) < 1e-13
+    lu_ref, piv_ref = lu_factor(A0, check_finite=False)
+    assert np.array_equal(piv, piv_ref[:k])                      # same pivot sequence as LAPACK's (partial pivoting is unique here)
+    assert rel(LU, lu_ref) < 1e-11

@@ -122,6 +122,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *                 blocks in one launch, one triangular GEMM), 0 = the reference's in-place recursion
  *   "inv_block"   Float32/Float16 solve: order of the diagonal blocks that are inverted once per call (FP64 128-blocks doubled in the next
  *                 wider type) so that a leaf is ONE triangular tcgen05 GEMM: 0 = default (1024), 128 = plain 128-wide leaves, powers of two up to 4096
+ *   "right_via_left" Float64, side 'R': 1 (default) = run the equivalent left-side problem (same Teff) on a transposed copy of B in the handle's
+ *                 workspace (n*m*8 bytes, at most 8 GiB) so that the fused slab kernel applies; 0 = the native right-side schedule
  *   "tc_persist"  Float16: 1 (default) = the persistent CTA-pair kernel (static tile list per cluster, two TMEM accumulators, 8 drain warps)
  *                 takes every multi-tile launch with K < 8192 and the block-inverse leaves; 0 = never; 2 = also the long updates
  *   "inv_dup"     1 (default) = an update also writes the block of B the next block-inverse leaf reads into the leaf's workspace (0: one copy per leaf)

@@ -57,6 +57,7 @@ struct nla_context {
   void* inv_acc; size_t inv_acc_bytes;     // block inverses / phase-1 products in the accumulation type (tri_inv.cuh)
   void* inv_u; size_t inv_u_bytes;
   int64_t pdl;
+  int64_t right_via_left;   // FP64 right side: 1 = solve the transposed (left-side) problem on a transposed copy of B
   int64_t tc_persist;   // Float16: 1 = persistent CTA-pair kernel (gemm_tc3.cuh) for every multi-tile launch
   int64_t inv_overlap;  // 1 = invert all but the first two blocks on a side stream while the solve is running
   cudaStream_t prep_stream; cudaEvent_t prep_event;
@@ -876,8 +877,45 @@ static int prepare_block_inverses(nla_context* ctx, const Problem& P, int64_t ib
   return NLA_OK;
 }
 
+// dst(c, r) = src(r, c): out-of-place transpose of a column-major rows x cols matrix (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) transpose_f64_kernel(const double* __restrict__ src, long long lds, double* __restrict__ dst, long long ldd,
+                                                            long long rows, long long cols) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32, c0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (r0 + tx < rows && c0 + j < cols) tile[j][tx] = src[(r0 + tx) + (c0 + j) * lds];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+    if (c0 + tx < cols && r0 + j < rows) dst[(c0 + tx) + (r0 + j) * ldd] = tile[tx][j];
+}
+
 template <typename T>
 static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream, const Gate* gate = nullptr) {
+  if constexpr (std::is_same<T, double>::value) {
+    // FP64, right side: X op(A) = alpha B  <=>  op(A)^T X^T = alpha B^T.  The fused slab kernel exists for the left side only, and FP64
+    // is so compute-bound (n flops per element of B) that two transposes of B are noise (n = m = 16384: 2 x 1.3 ms on a 130 ms solve),
+    // so the call runs as the left-side problem with the same Teff on a transposed copy of B in the handle's workspace.
+    const size_t need = (size_t)P.n * (size_t)P.m * sizeof(double);
+    if (P.right && ctx->right_via_left && !ctx->force_simt && ctx->encode && ctx->macro >= 8 && P.n % 8 == 0 && P.n >= 256 && P.m >= 128 &&
+        need <= ((size_t)8 << 30) && tma_ok(P.A, P.n, P.n, P.lda)) {
+      int wrc = grow_ws(ctx, &ctx->bcopy_ws, &ctx->bcopy_ws_bytes, need);
+      if (wrc != NLA_OK) return wrc;
+      double* ws = (double*)ctx->bcopy_ws;
+      dim3 g1((unsigned)((P.m + 31) / 32), (unsigned)((P.n + 31) / 32));   // B is m x n
+      transpose_f64_kernel<<<g1, 256, 0, stream>>>((const double*)P.B, P.ldb, ws, P.n, P.m, P.n);
+      ctx->launches++;
+      Problem L = P;
+      L.right = false; L.B = ws; L.ldb = P.n; L.es = 1; L.vs = P.n;   // teff_trans / lower already describe Teff, which is unchanged
+      int rc = rectrxm_typed<double>(ctx, L, stream, gate);
+      if (rc != NLA_OK) return rc;
+      dim3 g2((unsigned)((P.n + 31) / 32), (unsigned)((P.m + 31) / 32));
+      transpose_f64_kernel<<<g2, 256, 0, stream>>>(ws, P.n, (double*)P.B, P.ldb, P.n, P.m);
+      ctx->launches++;
+      NLA_CUDA(ctx, cudaGetLastError());
+      return NLA_OK;
+    }
+  }
   Plan plan;
   int prc = make_plan<T>(ctx, P, plan);
   if (prc != NLA_OK) return prc;
@@ -1011,7 +1049,7 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
-  ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
+  ctx->right_via_left = 1; ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
   ctx->inv_dup = 1; ctx->inv_block = 0; ctx->inv_acc = ctx->inv_u = nullptr; ctx->inv_acc_bytes = ctx->inv_u_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -1064,6 +1102,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "pdl")) { h->pdl = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_dup")) { h->inv_dup = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_overlap")) { h->inv_overlap = value != 0; return NLA_OK; }
+  if (!strcmp(key, "right_via_left")) { h->right_via_left = value != 0; return NLA_OK; }
   if (!strcmp(key, "tc_persist")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_persist = value; return NLA_OK; }
   if (!strcmp(key, "inv_block")) {
     if (value != 0 && (value < 128 || value > 4096 || (value & (value - 1)))) return NLA_ERR_INVALID_DIM;
@@ -1092,6 +1131,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "inv_dup")) return h->inv_dup;
   if (!strcmp(key, "inv_overlap")) return h->inv_overlap;
   if (!strcmp(key, "tc_persist")) return h->tc_persist;
+  if (!strcmp(key, "right_via_left")) return h->right_via_left;
   return -1;
 }
 

@@ -631,3 +631,27 @@ def test_recursive_lu_device_steps(nla, gpu, m, n):
     lu_ref, piv_ref = lu_factor(A0, check_finite=False)
     assert np.array_equal(piv, piv_ref[:k])                      # same pivot sequence as LAPACK's (partial pivoting is unique here)
     assert rel(LU, lu_ref) < 1e-11
+
+
+def test_right_side_via_left_fp64(nla, gpu):
+    """Float64, side 'R': the default runs the equivalent left-side problem on a transposed copy of B (fused slab kernel); option
+    right_via_left = 0 keeps the native right-side schedule.  Both against the oracle, every right-side variant, alpha != 1,
+    ragged m, a padded leading dimension, unit diagonal."""
+    n, m = 1536, 520
+    for uplo, trans, func in itertools.product(UPLOS, "NT", FUNCS):
+        A, B0 = rp.make_inputs(n, m, "R", uplo, np.float64, seed=91)
+        want = c_port.unified_rectrxm("R", uplo, trans, -0.75, func, A, B0.copy(order="F"))
+        assert gpu.get_option("right_via_left") == 1
+        gpu.launch_count(reset=True)
+        got = run_gpu(nla, "R", uplo, trans, -0.75, func, A, B0, ld_pad=2)
+        launches_via_left = gpu.launch_count()
+        gpu.set_option("right_via_left", 0)
+        try:
+            gpu.launch_count(reset=True)
+            native = run_gpu(nla, "R", uplo, trans, -0.75, func, A, B0, ld_pad=2)
+            launches_native = gpu.launch_count()
+        finally:
+            gpu.set_option("right_via_left", 1)
+        assert launches_via_left < launches_native          # 2 transposes + slab schedule instead of 128-wide leaves
+        assert rel(got, want) < 1e-13 and rel(native, want) < 1e-13, (uplo, trans, func)
+        assert rp.error_metric("R", uplo, trans, -0.75, func, A, B0, got) < 1e-13

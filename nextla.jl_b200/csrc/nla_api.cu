@@ -61,6 +61,7 @@ struct nla_context {
   int64_t tc_persist;   // Float16: 1 = persistent CTA-pair kernel (gemm_tc3.cuh) for every multi-tile launch
   int64_t inv_overlap;  // 1 = invert all but the first two blocks on a side stream while the solve is running
   cudaStream_t prep_stream; cudaEvent_t prep_event;
+  std::vector<cudaEvent_t> panel_prep_events;   // gated block-inverse solves: one per column panel of A
   int64_t inv_dup;      // 1 = updates also write the next leaf's block of V into the leaf workspace (0: explicit copy per leaf)
   int64_t tc_dbg;       // device pointer to per-CTA timing stamps (probes only)
   // device staging for the host-buffer entry point
@@ -432,6 +433,7 @@ struct TmaMaps {
   // block-inverse solve leaves (tri_inv.cuh): order of the inverted blocks (128 = plain tensor-core leaves) and the maps of the
   // copy of the leaf's block of V (the leaf GEMM is out of place); `Last` = the ragged last block (its K extent is the map's bound)
   int64_t ib, ws_ld;
+  const cudaEvent_t* leaf_events; int64_t leaf_event_cols;   // gated calls: event p = the block inverses of column panel p are ready
   int64_t late0, late1;   // ib-blocks [late0, late1) are being inverted on the side stream: wait for prep_event before their first leaf
   CUtensorMap mapS, mapS128, mapSLast, mapSLast128;
 };
@@ -613,6 +615,7 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
                    const Gate* gate = nullptr) {
   std::vector<char> waited(gate ? (size_t)gate->n_panels : 0, 0);
   bool late_waited = false;
+  std::vector<char> leaf_ev_waited;
   const Op* copied_leaf = nullptr;   // block-inverse leaf whose block of V the preceding update has already copied (GemmTcParams::dup)
   for (size_t oi = 0; oi < ops.size(); oi++) {
     const Op& o = ops[oi];
@@ -640,6 +643,14 @@ static int run_ops(nla_context* ctx, const Problem& P, const TmaMaps& maps, cons
       rc = launch_update<T>(ctx, P, maps, o, v0, nv, st, dup);
       copied_leaf = dup;
     } else if (maps.tc) {
+      if (maps.leaf_events) {
+        const size_t pp = (size_t)(o.off / maps.leaf_event_cols);
+        if (leaf_ev_waited.size() <= pp) leaf_ev_waited.resize(pp + 1, 0);
+        if (!leaf_ev_waited[pp]) {
+          NLA_CUDA(ctx, cudaStreamWaitEvent(st, maps.leaf_events[pp], 0));
+          leaf_ev_waited[pp] = 1;
+        }
+      }
       if (!late_waited && maps.late1 > maps.late0 && o.off / maps.ib >= maps.late0 && o.off / maps.ib < maps.late1) {
         NLA_CUDA(ctx, cudaStreamWaitEvent(st, ctx->prep_event, 0));
         late_waited = true;
@@ -682,6 +693,7 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, bool allow_
   std::vector<Op>& ops = plan.ops;
   TmaMaps& maps = plan.maps;
   maps.ok = false; maps.fused = false; maps.tc = false; maps.prep_per_leaf = false; maps.ib = DP_B; maps.ws_ld = 0; maps.late0 = maps.late1 = 0;
+  maps.leaf_events = nullptr; maps.leaf_event_cols = 0;
 
   // FP64 tensor-core path: both matrices must satisfy the TMA constraints (16-byte aligned base, even leading dimension,
   // row counts that are multiples of 8); otherwise the generic strided kernels take the call.
@@ -923,7 +935,11 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
   const TmaMaps& maps = plan.maps;
   if constexpr (!std::is_same<T, double>::value) {
     if (maps.tc) {  // prepare every diagonal block once, ahead of the schedule (and of the fork into RHS slabs)
-      if (gate) {   // the preparation reads the whole diagonal: all of A must have arrived
+      // A arriving in panels (nla_rectrxm_gated): a block-inverse solve prepares the diagonal blocks of a panel as soon as that panel is
+      // there (side stream, panels in consumption order, one event per panel for the leaves); everything else reads the whole diagonal up
+      // front and has to wait for all of A.
+      const bool panel_prep = gate && P.solve && maps.ib > DP_B && gate->panel_cols % maps.ib == 0;
+      if (gate && !panel_prep) {
         std::vector<char> waited((size_t)gate->n_panels, 0);
         int grc = gate_wait(ctx, gate, waited, 0, P.n, stream);
         if (grc != NLA_OK) return grc;
@@ -931,7 +947,29 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
       }
       const int64_t t_rs = P.teff_trans ? P.lda : 1, t_cs = P.teff_trans ? 1 : P.lda;
       int rc;
-      if (maps.ib > DP_B) {
+      if (panel_prep) {
+        if (!ctx->prep_stream) {
+          NLA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+          NLA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
+        }
+        while ((int64_t)ctx->panel_prep_events.size() < gate->n_panels) {
+          cudaEvent_t e;
+          NLA_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          ctx->panel_prep_events.push_back(e);
+        }
+        NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));                      // the workspaces may still be in use by an earlier call
+        NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->fork_event, 0));
+        const int64_t bpp = gate->panel_cols / maps.ib, np = (P.n + gate->panel_cols - 1) / gate->panel_cols;
+        rc = NLA_OK;
+        for (int64_t q = 0; q < np && rc == NLA_OK; q++) {
+          const int64_t pp = P.lower ? q : np - 1 - q;                                 // consumption order of a solve
+          NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, gate->events[pp], 0));
+          rc = prepare_block_inverses<T>(ctx, P, maps.ib, ctx->prep_stream, pp * bpp, (pp + 1) * bpp);
+          if (rc == NLA_OK) NLA_CUDA(ctx, cudaEventRecord(ctx->panel_prep_events[(size_t)pp], ctx->prep_stream));
+        }
+        plan.maps.leaf_events = ctx->panel_prep_events.data();
+        plan.maps.leaf_event_cols = gate->panel_cols;
+      } else if (maps.ib > DP_B) {
         // the first two blocks the schedule consumes are inverted here; the others on a side stream, overlapped with the first
         // leaves and updates (run_ops waits for prep_event before the first leaf that needs them)
         const int64_t nb = (P.n + maps.ib - 1) / maps.ib, ga = 2;
@@ -1079,6 +1117,7 @@ int nla_destroy(nla_handle_t h) {
   if (h->bcopy_ws) cudaFree(h->bcopy_ws);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
+  for (auto e : h->panel_prep_events) cudaEventDestroy(e);
   if (h->inv_acc) cudaFree(h->inv_acc);
   if (h->inv_u) cudaFree(h->inv_u);
   h->magic = 0;

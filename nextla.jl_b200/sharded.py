@@ -90,7 +90,9 @@ def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float
     n = A.shape[0]
     if not (A.dim() == 2 and A.stride(0) == 1 and A.stride(1) == n):
         raise ValueError("pipelined broadcast needs a column-major A with leading dimension n")
-    pc, npan = panel_geometry(n, panels)
+    # panels that are a multiple of 1024 columns (the block-inverse order) let the Float32/Float16 solves prepare their diagonal blocks
+    # panel by panel instead of waiting for all of A
+    pc, npan = panel_geometry(n, panels, gran=1024 if n >= 1024 * panels else 128)
     order = panel_order(side, uplo, transpose, func, n, pc)
     dev = A.device
     if dev not in _side_streams:

@@ -473,14 +473,16 @@ def test_block_inverse_leaves(nla, gpu, dtype, ib):
         gpu.set_option("inv_block", 0)
 
 
-@pytest.mark.parametrize("dtype", [np.float64, np.float16])
-@pytest.mark.parametrize("side,uplo,trans,func", [("L", "L", "N", "S"), ("L", "U", "N", "S"), ("R", "L", "T", "M"), ("L", "L", "T", "S")])
-def test_gated_arrival_of_A(nla, gpu, dtype, side, uplo, trans, func):
+@pytest.mark.parametrize("dtype,pc", [(np.float64, 512), (np.float16, 512), (np.float16, 1024), (np.float32, 1024)])
+@pytest.mark.parametrize("side,uplo,trans,func", [("L", "L", "N", "S"), ("L", "U", "N", "S"), ("R", "L", "T", "M"), ("L", "L", "T", "S"), ("R", "U", "N", "S")])
+def test_gated_arrival_of_A(nla, gpu, dtype, pc, side, uplo, trans, func):
     """nla_rectrxm_gated: A becomes valid panel by panel (here: copied on a side stream from a pristine matrix, each panel behind a
     spin kernel so that the solve really has to wait), result identical to the plain call."""
     import torch
 
-    n, m, pc = 2048, 384, 512
+    # (panels that are a multiple of the block-inverse order let the Float32/Float16 solves prepare each panel's diagonal blocks as it
+    #  arrives; otherwise, and for multiplies, they wait for all of A first)
+    n, m = 3072 if pc == 1024 else 2048, 384
     A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=31, recipe="scaled")
     dA_full = nla.colmajor(A)
     want = run_gpu(nla, side, uplo, trans, 1.25, func, A, B0)

@@ -289,8 +289,16 @@ def main():
         if world > 1:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tt = tmax.item()
+        # bytes actually copied: only the referenced triangle of A crosses PCIe -- as 1024 x 1024 tiles on or below the diagonal
+        # (nla_rectrxm_host) or as the trapezoid of each of the 8 column panels (multi-GPU path) -- plus every rank's B in and out
+        if world == 1:
+            nt = -(-n // 1024)
+            a_bytes = sum(min(1024, n - i * 1024) * min(1024, n - j * 1024) for i in range(nt) for j in range(i + 1)) * es
+        else:
+            pc, npan = sharded.panel_geometry(n, 8)
+            a_bytes = sum((n - p * pc) * (min(n, (p + 1) * pc) - p * pc) for p in range(npan)) * es
         e2e = {"value": e2e_steps * flops_per_step_all / tt * 1e-12, "unit": UNIT,
-               "h2d_bytes_per_step": (n * n + n * m * world) * es, "d2h_bytes_per_step": n * m * world * es, "steps": e2e_steps,
+               "h2d_bytes_per_step": a_bytes + n * m * world * es, "d2h_bytes_per_step": n * m * world * es, "steps": e2e_steps,
                "ms_per_step": tt / e2e_steps * 1e3, "api": "nla_rectrxm_host (pinned host A and B in, B out)" if world == 1 else
                "sharded.unified_rectrxm_pipelined_host: H2D(A panels) + ncclBroadcast per panel + nla_rectrxm_hostb_gated (B streamed in chunks, launches gated on the panels of A)"}
         # check the e2e result too

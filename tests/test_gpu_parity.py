@@ -657,3 +657,25 @@ def test_right_side_via_left_fp64(nla, gpu):
         assert launches_via_left < launches_native          # 2 transposes + slab schedule instead of 128-wide leaves
         assert rel(got, want) < 1e-13 and rel(native, want) < 1e-13, (uplo, trans, func)
         assert rp.error_metric("R", uplo, trans, -0.75, func, A, B0, got) < 1e-13
+
+
+def test_options_round_trip(nla, gpu):
+    """Every tunable documented in include/nextla_b200.h can be set and read back; unknown keys and out-of-range values are status
+    codes, not crashes; defaults are restored."""
+    import re
+
+    header = open(nla.HEADER_PATH).read()
+    keys = re.findall(r'^ \*   "([a-z0-9_]+)"', header, flags=re.M)
+    assert {"leaf", "macro", "streams", "tc_bn", "tc_cg", "inv_block", "tc_persist", "right_via_left", "trmm_batched", "pdl", "profile"} <= set(keys)
+    for k in keys:
+        old = gpu.get_option(k)
+        assert old >= 0, k
+        gpu.set_option(k, old)
+        assert gpu.get_option(k) == old, k
+    with pytest.raises(nla.NextLAError):
+        gpu.set_option("no_such_option", 1)
+    for k, bad in (("inv_block", 300), ("tc_bn", 64), ("tc_cg", 7), ("streams", 99), ("tc_persist", 5)):
+        old = gpu.get_option(k)
+        with pytest.raises(nla.NextLAError):
+            gpu.set_option(k, bad)
+        assert gpu.get_option(k) == old

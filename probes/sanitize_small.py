@@ -1,0 +1,33 @@
+# Small end-to-end pass over the newer kernels (block inverses, persistent pair kernel incl. edge tiles, dup epilogue, transposed
+# right side, laswp, unit diagonal) meant to be run under `compute-sanitizer --tool memcheck`.
+import itertools, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import __graft_entry__ as ge
+from oracle import reference_port as rp
+nla = ge.load_package(); h = nla.default_handle(0)
+worst = 0.0
+for dtype, tol in ((np.float16, 1e-2), (np.float32, 1e-5), (np.float64, 1e-13)):
+    for (n, m) in ((1300, 200), (2304, 136)):
+        for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=3, recipe="scaled")
+            dA, dB = nla.colmajor(A), nla.colmajor(B0)
+            nla.unified_trxm(side, uplo, trans, "N", 1.5, func, dA, dB); torch.cuda.synchronize()
+            err = rp.error_metric(side, uplo, trans, 1.5, func, A, B0, nla.to_numpy(dB))
+            assert err < tol, (dtype, n, m, side, uplo, trans, func, err)
+            worst = max(worst, err / tol)
+# GEMM shapes with ragged edges through the persistent kernel
+rng = np.random.RandomState(0)
+for (M, N, K) in ((384, 520, 320), (1000, 1544, 200)):
+    A = (rng.rand(M, K) - 0.5).astype(np.float16); B = (rng.rand(K, N) - 0.5).astype(np.float16); C = rng.rand(M, N).astype(np.float16)
+    dC = nla.colmajor(np.asfortranarray(C)); nla.GEMM_SUB(dC, nla.colmajor(np.asfortranarray(A)), nla.colmajor(np.asfortranarray(B))); torch.cuda.synchronize()
+    want = C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)
+    assert np.linalg.norm(nla.to_numpy(dC) - want) / np.linalg.norm(want) < 1e-3
+# laswp
+A = rng.rand(300, 70); dA = nla.colmajor(A); piv = torch.from_numpy(rng.randint(1, 301, size=300).astype(np.int64)).cuda()
+nla.laswp(dA, 1, 300, piv, 1); torch.cuda.synchronize()
+ref = A.copy()
+for i, p in enumerate(piv.cpu().numpy()):
+    ref[[i, p - 1]] = ref[[p - 1, i]]
+assert np.array_equal(nla.to_numpy(dA), ref)
+print("sanitize_small ok, worst err/tol", worst)

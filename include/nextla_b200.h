@@ -81,8 +81,9 @@ int nla_rectrxm_hostb_gated(nla_handle_t handle, char side, char uplo, char tran
                             double alpha, const void *A_dev, int64_t lda, void *B_host, int64_t ldb, int64_t panel_cols,
                             int64_t n_panels, void *const *panel_events);
 
-/* Strided (pitched) asynchronous copy between pinned host memory and the device on `stream` -- what the multi-GPU driver uses to
- * upload only the referenced triangle of a column panel of A (a trapezoid: `height` columns of `width_bytes` each). */
+/* Strided (pitched) asynchronous copy on `stream`: to_device = 1 host -> device, 0 device -> host, 2 device -> device.  The multi-GPU
+ * driver uses it to upload, and to pack / unpack for the broadcast, only the referenced triangle of a column panel of A (a trapezoid:
+ * `height` columns of `width_bytes` each). */
 int nla_memcpy2d_async(nla_handle_t handle, void *dst, int64_t dst_pitch_bytes, const void *src, int64_t src_pitch_bytes,
                        int64_t width_bytes, int64_t height, int to_device, void *stream);
 

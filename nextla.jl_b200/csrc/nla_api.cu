@@ -1552,8 +1552,9 @@ int nla_memcpy2d_async(nla_handle_t h, void* dst, int64_t dst_pitch_bytes, const
   if (width_bytes == 0 || height == 0) return NLA_OK;
   if (!dst || !src) return NLA_ERR_NULL_POINTER;
   NLA_CUDA(h, cudaSetDevice(h->device));
-  NLA_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height,
-                                to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  const cudaMemcpyKind kind = to_device == 2 ? cudaMemcpyDeviceToDevice : to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  NLA_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height, kind,
+                                (cudaStream_t)stream));
   return NLA_OK;
 }
 

@@ -73,10 +73,42 @@ def broadcast_panels(A_storage, order, panel_cols: int, src: int = 0, group=None
 
 
 _side_streams = {}
+_stage = {}
+
+
+def broadcast_panel_triangle(A_store, uplo: str, p: int, pc: int, src: int, group, stream, handle):
+    """Broadcast only the referenced part of column panel p of A (CUDA): rows [p*pc, n) of a lower panel, [0, (p+1)*pc) of an upper
+    one -- a trapezoid that is strided in memory, so the owner packs it into a contiguous staging buffer (pitched device copy), NCCL
+    moves that, and the receivers unpack.  Halves the bytes on the wire, but measured SLOWER than whole panels on NVLink 5 (C4 at 8
+    GPUs 19.4 vs 18.6 ms, at 2 GPUs 70.4 vs 66.1 ms: the pack / unpack copies compete with the solve for HBM and SMs), so
+    unified_rectrxm_pipelined keeps whole panels by default and this stays an option (`triangle_only=True`) for slower links."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _check, load_library
+
+    n = A_store.shape[0]
+    c0, c1 = p * pc, min(n, (p + 1) * pc)
+    r0, r1 = (c0, n) if uplo == "L" else (0, c1)
+    w, cols, es = r1 - r0, c1 - c0, A_store.element_size()
+    key = (A_store.device, A_store.dtype)
+    if key not in _stage or _stage[key].numel() < n * pc:
+        _stage[key] = torch.empty(n * pc, dtype=A_store.dtype, device=A_store.device)
+    flat = _stage[key][:w * cols]
+    lib, rank = load_library(), dist.get_rank(group)
+    panel_ptr = A_store.data_ptr() + (c0 * n + r0) * es
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    if rank == src:
+        _check(lib.nla_memcpy2d_async(handle._h, flat.data_ptr(), w * es, panel_ptr, n * es, w * es, cols, 2, sp), handle._h)
+    dist.broadcast(flat, src=src, group=group)
+    if rank != src:
+        _check(lib.nla_memcpy2d_async(handle._h, panel_ptr, n * es, flat.data_ptr(), w * es, w * es, cols, 2, sp), handle._h)
 
 
 def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float, func: str, A, B_local, src: int = 0, group=None,
-                              panels: int = 8, handle=None):
+                              panels: int = 8, handle=None, triangle_only: bool = False):
     """Multi-GPU call with the broadcast of A overlapped with the solve: A travels over NCCL in column
     panels, in the order the schedule consumes them, on a side stream; the solve runs on the current stream and waits for
     each panel right before the first kernel that reads it (nla_rectrxm_gated).  CUDA only."""
@@ -100,8 +132,16 @@ def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float
     bs = _side_streams[dev]
     events = [torch.cuda.Event() for _ in range(npan)]
     bs.wait_stream(torch.cuda.current_stream(dev))   # earlier work on the caller's stream may still be using A
+    from . import default_handle
+
+    h = handle or default_handle(dev.index)
     with torch.cuda.stream(bs):
-        broadcast_panels(A.t(), order, pc, src=src, group=group, on_panel=lambda p: events[p].record(bs))
+        if triangle_only:   # pack / broadcast / unpack only the trapezoid of each panel that the `uplo` triangle covers
+            for p in order:
+                broadcast_panel_triangle(A.t(), uplo, p, pc, src, group, bs, h)
+                events[p].record(bs)
+        else:
+            broadcast_panels(A.t(), order, pc, src=src, group=group, on_panel=lambda p: events[p].record(bs))
     empty = B_local.shape[1] == 0 if side == "L" else B_local.shape[0] == 0
     if empty:
         torch.cuda.current_stream(dev).wait_stream(bs)

@@ -11,7 +11,7 @@ from importlib import import_module
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C4"); ap.add_argument("--steps", type=int, default=3); ap.add_argument("--warmup", type=int, default=2)
-ap.add_argument("--no-pipeline", action="store_true")
+ap.add_argument("--no-pipeline", action="store_true"); ap.add_argument("--triangle", type=int, default=-1, help="1/0: broadcast only the referenced triangle of each panel (default: library default)")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
@@ -42,7 +42,8 @@ X = torch.empty(shape[::-1], dtype=dt, device=dev).t()
 
 def step():
     if world > 1 and not a.no_pipeline:
-        sh.unified_rectrxm_pipelined(side, uplo, trans, 1.0, func, A, X, src=0, panels=8, handle=h)
+        kw = {} if a.triangle < 0 else {"triangle_only": bool(a.triangle)}
+        sh.unified_rectrxm_pipelined(side, uplo, trans, 1.0, func, A, X, src=0, panels=8, handle=h, **kw)
     else:
         if world > 1:
             dist.broadcast(A.t(), src=0)
@@ -79,7 +80,7 @@ if world > 1:
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"config": a.config, "n_gpus": world, "dtype": str(dt), "case": side + uplo + trans + func, "n": n, "rhs_total": m_total, "rhs_per_gpu": m,
-                      "ms_per_step": round(ms, 3), "tflops_total": round(float(n) * n * m_total / ms * 1e-9, 1), "broadcast": "blocking" if a.no_pipeline else "8 panels pipelined",
+                      "ms_per_step": round(ms, 3), "tflops_total": round(float(n) * n * m_total / ms * 1e-9, 1), "broadcast": "blocking" if a.no_pipeline else "8 panels pipelined", "triangle_only": a.triangle,
                       "backward_error_max_over_ranks": err.item(), "tolerance": tol}), flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

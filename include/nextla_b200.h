@@ -137,6 +137,7 @@ int64_t nla_get_option(nla_handle_t handle, const char *key);
 /* Host-only introspection of the schedule that replaces the recursive splitter (src/rectrxm.jl:101-198): writes up to
  * max_ops records of 6 int64 {kind (0 = leaf, 1 = GEMM update), c0, cn, k0, kn, carries_alpha} in launch order, in the
  * normalised coordinates of DESIGN.md (leaf: diagonal block [c0, c0+cn); update: V[c0:c0+cn] +-= Teff[c,k] V[k0:k0+kn]).
+ * `leaf` = recursion cutoff: <= 0 -> 128; up to 4096 (2048 = the fused FP64 slab schedule, 1024 = the block-inverse Float32/Float16 one).
  * Returns the number of ops (may exceed max_ops) or a negative nla_status.  Needs no GPU. */
 int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t *ops, int64_t max_ops);
 

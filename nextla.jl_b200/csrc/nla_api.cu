@@ -1204,7 +1204,7 @@ int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t
   if (n == 0) return 0;
   if (leaf <= 0) leaf = LEAF_MAX;
   std::vector<Op> ops;
-  build_schedule(P, std::min<int64_t>(leaf, LEAF_MAX), 0, n, false, true, ops);
+  build_schedule(P, std::min<int64_t>(leaf, 4096), 0, n, false, true, ops);   // cutoffs above LEAF_MAX: fused slab / block-inverse schedules
   for (size_t i = 0; i < ops.size() && (int64_t)i < max_ops && out; i++) {
     const Op& o = ops[i];
     int64_t* r = out + 6 * i;

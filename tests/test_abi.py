@@ -137,3 +137,24 @@ def test_panel_order_follows_the_schedule(nla):
     assert nla.panel_order("L", "L", "N", "S", 0, 256) == []
     with pytest.raises(nla.NextLAError):
         nla.panel_order("X", "L", "N", "S", 100, 10)
+
+
+@pytest.mark.parametrize("n", [1024, 3000, 4096, 5000, 16384, 20000])
+@pytest.mark.parametrize("cutoff", [1024, 2048])
+def test_large_cutoff_schedule_invariants(nla, n, cutoff):
+    """What the fused FP64 slab (cutoff 2048) and the block-inverse Float32/Float16 leaves (cutoff 1024) rely on, for every variant
+    and ragged orders: (1) the schedule is still the reference recursion (src/rectrxm.jl:129-134 split rule) with that threshold;
+    (2) every leaf starts at a multiple of the cutoff and only the last block along the diagonal is ragged (the inverse workspace
+    is indexed by block); (3) in a solve, a leaf that follows an update lies inside that update's output range (the update's epilogue writes
+    the leaf's copy of V, GemmTcParams::dup); (4) the ops of a solve partition the flops n^2 exactly."""
+    for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+        ops = nla.plan(side, uplo, trans, func, n, cutoff)
+        assert [p[:5] for p in ops] == _reference_trace(side, uplo, trans, func, n, cutoff)
+        leaves = sorted((c0, cn) for kind, c0, cn, k0, kn, _ in ops if kind == 0)
+        assert [c0 for c0, _ in leaves] == list(range(0, n, cutoff))
+        assert all(cn == cutoff for _, cn in leaves[:-1]) and leaves[-1][1] == n - leaves[-1][0]
+        for prev, cur in zip(ops, ops[1:]):
+            if cur[0] == 0 and prev[0] == 1:
+                assert prev[1] <= cur[1] and cur[1] + cur[2] <= prev[1] + prev[2], (side, uplo, trans, func, prev, cur)
+        flops = sum(cn * cn if kind == 0 else 2 * cn * kn for kind, c0, cn, k0, kn, _ in ops)
+        assert flops == n * n

@@ -15,6 +15,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
+#include "gemm_tc4.cuh"
 #include "diag_prep.cuh"
 #include "tri_inv.cuh"
 #include "laswp.cuh"
@@ -57,6 +58,7 @@ struct nla_context {
   void* inv_acc; size_t inv_acc_bytes;     // block inverses / phase-1 products in the accumulation type (tri_inv.cuh)
   void* inv_u; size_t inv_u_bytes;
   int64_t pdl;
+  int64_t tc_wide_k;    // Float16: updates with K >= this run on 256 x 512 pair tiles (gemm_tc4.cuh); 0 = never
   int64_t right_via_left;   // FP64 right side: 1 = solve the transposed (left-side) problem on a transposed copy of B
   int64_t tc_persist;   // Float16: 1 = persistent CTA-pair kernel (gemm_tc3.cuh) for every multi-tile launch
   int64_t inv_overlap;  // 1 = invert all but the first two blocks on a side stream while the solve is running
@@ -340,6 +342,28 @@ static int launch_gemm_tc3_variant(nla_context* ctx, const CUtensorMap& mA, cons
   return NLA_OK;
 }
 
+// Persistent CTA-pair variant with 256 x 512 tiles (gemm_tc4.cuh, Float16, long updates)
+template <int AMAJ, int BMAJ>
+static int launch_gemm_tc4_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB128, const GemmTcParams& gp, cudaStream_t st) {
+  static bool configured[64] = {false};
+  if (!configured[ctx->device & 63]) {
+    NLA_CUDA(ctx, (cudaFuncSetAttribute(gemm_tc4_kernel<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc4Shape::SMEM)));
+    configured[ctx->device & 63] = true;
+  }
+  const int64_t ntiles = (int64_t)((gp.tiles_m + 1) / 2) * gp.tiles_n;
+  const int64_t ncl = std::min<int64_t>(ntiles, std::max(1, ctx->sm_count / 2));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * ncl)); cfg.blockDim = dim3(Tc4Shape::THREADS);
+  cfg.dynamicSmemBytes = Tc4Shape::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = ctx->pdl ? 1 : 0;
+  NLA_CUDA(ctx, (cudaLaunchKernelEx(&cfg, gemm_tc4_kernel<AMAJ, BMAJ>, mA, mB128, gp)));
+  ctx->launches++;
+  return NLA_OK;
+}
+
 // N tile of a launch: 256 unless that grid would leave SMs idle
 static int tc_pick_bn(nla_context* ctx, int64_t M, int64_t N) {
   if (ctx->tc_bn == 128 || ctx->tc_bn == 256) return (int)ctx->tc_bn;
@@ -368,6 +392,14 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
   gp.chunk_k = (int)ctx->tc_chunk_k;
   gp.dbg = (unsigned long long*)ctx->tc_dbg;
   if constexpr (sizeof(T) == 2) {
+    // Float16, long updates: 256 x 512 pair tiles (two accumulators share the A tile: 171 instead of 128 flop per byte of L2 traffic)
+    if (ctx->tc_wide_k > 0 && gp.win_mode == 0 && gp.K >= ctx->tc_wide_k && gp.M >= 256 && gp.N >= 512 && !force_bn && ctx->tc_bn == 0 &&
+        ctx->tc_cg != 1) {
+      gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + 511) / 512;
+      if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc4_variant<MAJ_MN, MAJ_K>(ctx, mA, mB128, gp, st);
+      if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc4_variant<MAJ_K, MAJ_K>(ctx, mA, mB128, gp, st);
+      if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc4_variant<MAJ_MN, MAJ_MN>(ctx, mA, mB128, gp, st);
+    }
     // Float16: the persistent CTA-pair kernel takes every launch with more than one M tile whose K windows it knows
     // (none, or the block-inverse leaves' 4 / 5 -- for those a forced 128-wide N tile is a constraint of the one-tile kernels only)
     const bool win_ok = gp.win_mode == 0 || gp.win_mode == 4 || gp.win_mode == 5;
@@ -1087,7 +1119,7 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
-  ctx->right_via_left = 1; ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
+  ctx->tc_wide_k = 4096; ctx->right_via_left = 1; ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
   ctx->inv_dup = 1; ctx->inv_block = 0; ctx->inv_acc = ctx->inv_u = nullptr; ctx->inv_acc_bytes = ctx->inv_u_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -1142,6 +1174,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "inv_dup")) { h->inv_dup = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_overlap")) { h->inv_overlap = value != 0; return NLA_OK; }
   if (!strcmp(key, "right_via_left")) { h->right_via_left = value != 0; return NLA_OK; }
+  if (!strcmp(key, "tc_wide_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_wide_k = value; return NLA_OK; }
   if (!strcmp(key, "tc_persist")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_persist = value; return NLA_OK; }
   if (!strcmp(key, "inv_block")) {
     if (value != 0 && (value < 128 || value > 4096 || (value & (value - 1)))) return NLA_ERR_INVALID_DIM;
@@ -1171,6 +1204,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "inv_overlap")) return h->inv_overlap;
   if (!strcmp(key, "tc_persist")) return h->tc_persist;
   if (!strcmp(key, "right_via_left")) return h->right_via_left;
+  if (!strcmp(key, "tc_wide_k")) return h->tc_wide_k;
   return -1;
 }
 

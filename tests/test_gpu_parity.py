@@ -679,3 +679,33 @@ def test_options_round_trip(nla, gpu):
         with pytest.raises(nla.NextLAError):
             gpu.set_option(k, bad)
         assert gpu.get_option(k) == old
+
+
+def test_wide_pair_kernel(nla, gpu):
+    """The 256 x 512 persistent pair kernel (csrc/gemm_tc4.cuh: two accumulators share the A tile, Float16, long updates) forced on
+    from K = 64 (option tc_wide_k): updates with one tile, more tiles than clusters, ragged M/N/K and N that is not a multiple of 512,
+    every majorness instantiation, against FP64 truth; then every solve / multiply variant so that the `dup` epilogue (the update that
+    precedes a block-inverse leaf) and the edge path run through it too."""
+    import torch
+
+    dtype = np.float16
+    rng = np.random.RandomState(33)
+    assert gpu.get_option("tc_wide_k") == 4096
+    gpu.set_option("tc_wide_k", 64)
+    try:
+        for (M, N, K) in [(256, 512, 64), (384, 1100, 320), (1000, 1544, 1096), (4096, 9000, 512), (512, 1024, 4160)]:
+            A = (rng.rand(M, K) - 0.5).astype(dtype); B = (rng.rand(K, N) - 0.5).astype(dtype); C = rng.rand(M, N).astype(dtype)
+            want = C.astype(np.float64) - A.astype(np.float64) @ B.astype(np.float64)
+            for ta, tb in (("N", "N"), ("T", "N"), ("N", "T")):
+                Ain = np.asfortranarray(A.T.copy() if ta == "T" else A); Bin = np.asfortranarray(B.T.copy() if tb == "T" else B)
+                dC = nla.colmajor(np.asfortranarray(C))
+                nla._gemm(dC, nla.colmajor(Ain), nla.colmajor(Bin), -1, transa=ta, transb=tb); torch.cuda.synchronize()
+                assert rel(nla.to_numpy(dC), want) < 1e-3, (M, N, K, ta, tb)
+        for n, m in ((1500, 520), (3000, 1030)):
+            for side, uplo, trans, func in itertools.product(SIDES, UPLOS, "NT", FUNCS):
+                A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=n + 2, recipe="scaled")
+                got = run_gpu(nla, side, uplo, trans, 1.5, func, A, B0)
+                assert np.isfinite(got).all()
+                assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (n, m, side, uplo, trans, func)
+    finally:
+        gpu.set_option("tc_wide_k", 4096)

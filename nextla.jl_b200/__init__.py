@@ -11,6 +11,7 @@ Function names and argument order follow the reference:
   GEMM_ADD(A, B, C)  (C += A*B),  GEMM_SUB(A, B, C)  (A -= B*C) <- src/matmul.jl:69-81
   trsm(side, uplo, transa, diag, A, B, alpha), trmm(...)       <- src/trsm.jl:186-205, src/trmm.jl:430-448
   laswp(A, first, last, ipiv, incx), getrf2_update(A, n1, ipiv) <- src/lu.jl:470-530, :274-280 (the device steps of the recursive LU)
+  lauum(uplo, A, ib)                                            <- src/lauum.jl:52-186 (block loop; O(n^3) steps on this library's kernels)
 
 Matrices are column-major device arrays: 2-D torch CUDA tensors with stride (1, ld) (use `colmajor()` /
 `to_numpy()`).  Everything runs on the GPU through the library; there is NO CPU fallback -- importing is fine
@@ -360,6 +361,49 @@ def getrf2_update(A, n1: int, ipiv, **kw):
     trsm("L", "L", "N", "U", A[:n1, :n1], A[:n1, n1:], 1.0, **kw)        # src/lu.jl:277
     if m > n1:
         GEMM_SUB(A[n1:, n1:], A[n1:, :n1], A[:n1, n1:], **kw)            # src/lu.jl:280
+    return A
+
+
+def lauum(uplo: str, A, ib: int = 1024, **kw):
+    """lauum!(uplo, n, A, ib) -- src/lauum.jl:52-186: A := L^H * L (uplo 'L') or U * U^H (uplo 'U'), the triangular factor stored in
+    the `uplo` triangle of the device matrix A, result in the same triangle; the opposite triangle is neither read nor written
+    (the reference multiplies the full diagonal blocks, i.e. assumes it is zero).  Block loop of the reference with its O(n^3) steps
+    on this library's kernels: the off-diagonal block row/column through trmm (nla_trxm) and GEMM_ADD (nla_gemm_update); the
+    ib x ib diagonal blocks through trmm / GEMM_ADD into a scratch block whose triangle is merged back with torch.tril / triu
+    (SURVEY.md 8(f3))."""
+    import torch
+
+    n = A.shape[0]
+    if uplo not in ("L", "U"):
+        raise NextLAError("uplo must be 'L' or 'U'")          # src/lauum.jl:54
+    if A.shape[1] != n:
+        raise NextLAError("A must be square")
+    lower = uplo == "L"
+    tri, anti = (torch.tril, torch.triu) if lower else (torch.triu, torch.tril)
+    for i0 in range(0, n, ib):
+        b = min(ib, n - i0)
+        i1 = i0 + b
+        Aii = A[i0:i1, i0:i1]
+        tmp = torch.zeros((b, b), dtype=A.dtype, device=A.device).t()      # column-major scratch
+        if lower:
+            if i0 > 0:
+                trmm("L", "L", "T", "N", Aii, A[i0:i1, :i0], 1.0, **kw)     # A[i, :i0] = L_ii^H A[i, :i0]              (:165)
+            tmp.copy_(tri(Aii))
+            trmm("L", "L", "T", "N", Aii, tmp, 1.0, **kw)                   # L_ii^H L_ii                                (:169-172)
+            if i1 < n:
+                if i0 > 0:
+                    GEMM_ADD(A[i1:, i0:i1], A[i1:, :i0], A[i0:i1, :i0], transa="T", **kw)   # += A[i1:, i]^H A[i1:, :i0]   (:177)
+                GEMM_ADD(A[i1:, i0:i1], A[i1:, i0:i1], tmp, transa="T", **kw)               # rank-k update of the block    (:180-183)
+        else:
+            if i0 > 0:
+                trmm("R", "U", "T", "N", Aii, A[:i0, i0:i1], 1.0, **kw)     # A[:i0, i] = A[:i0, i] U_ii^H              (:110)
+            tmp.copy_(tri(Aii))
+            trmm("R", "U", "T", "N", Aii, tmp, 1.0, **kw)                   # U_ii U_ii^H                                (:114-118)
+            if i1 < n:
+                if i0 > 0:
+                    GEMM_ADD(A[:i0, i1:], A[i0:i1, i1:], A[:i0, i0:i1], transb="T", **kw)   # += A[:i0, i1:] A[i, i1:]^H   (:124)
+                GEMM_ADD(A[i0:i1, i1:], A[i0:i1, i1:], tmp, transb="T", **kw)               # rank-k update                (:127-131)
+        Aii.copy_(tri(tmp) + anti(Aii, 1 if lower else -1))
     return A
 
 

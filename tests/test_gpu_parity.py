@@ -709,3 +709,27 @@ def test_wide_pair_kernel(nla, gpu):
                 assert rp.error_metric(side, uplo, trans, 1.5, func, A, B0, got) < TOL[dtype], (n, m, side, uplo, trans, func)
     finally:
         gpu.set_option("tc_wide_k", 4096)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5)])
+@pytest.mark.parametrize("n,ib", [(96, 32), (1000, 256), (2048, 1024)])
+def test_lauum_block_loop(nla, gpu, dtype, tol, n, ib):
+    """lauum! (src/lauum.jl:52-186) as the reference's block loop on this library's trmm / GEMM kernels: L^H L and
+    U U^H against NumPy; the opposite triangle (NaN here) is neither read nor written."""
+    import torch
+
+    rng = np.random.RandomState(n + ib)
+    F = (rng.rand(n, n) - 0.5).astype(dtype) / np.sqrt(n) + np.eye(n, dtype=dtype)
+    for uplo in "LU":
+        T = np.tril(F) if uplo == "L" else np.triu(F)
+        want = (T.astype(np.float64).T @ T.astype(np.float64)) if uplo == "L" else (T.astype(np.float64) @ T.astype(np.float64).T)
+        Ain = T.copy()
+        Ain[np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)] = np.nan
+        dA = nla.colmajor(Ain)
+        nla.lauum(uplo, dA, ib)
+        torch.cuda.synchronize()
+        got = nla.to_numpy(dA)
+        mask = np.tril(np.ones((n, n), bool)) if uplo == "L" else np.triu(np.ones((n, n), bool))
+        assert np.isnan(got[~mask]).all()                       # untouched
+        assert np.isfinite(got[mask]).all()
+        assert np.linalg.norm(got[mask] - want[mask]) / np.linalg.norm(want[mask]) < tol, uplo

@@ -145,7 +145,8 @@ int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t
 
 /* Per-launch device times recorded while option "profile" is 1: waits for the recorded work, writes up to max_records
  * records of 3 doubles {kind (0 = leaf, 1 = GEMM update), algorithmic flops of the launch, milliseconds} in launch order,
- * clears the log and returns the number of records that were available (or a negative nla_status). */
+ * clears the log and returns the number of records that were available (or a negative nla_status).  If there is room, one more record
+ * of kind 2 follows: the device time from the start of the first launch to the end of the last (launches + the gaps between them). */
 int64_t nla_profile_read(nla_handle_t handle, double *records, int64_t max_records);
 
 /* Counters for bench.py: kernels launched by this handle since the last reset. */

@@ -1218,10 +1218,20 @@ int64_t nla_profile_read(nla_handle_t h, double* records, int64_t max_records) {
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.e0, pr.e1);
     if (e != cudaSuccess) { h->last_cuda = (int)e; return -NLA_ERR_CUDA; }
     if (records && i < max_records) { records[3 * i] = pr.kind; records[3 * i + 1] = pr.flops; records[3 * i + 2] = ms; }
-    h->prof_pool.push_back(pr.e0); h->prof_pool.push_back(pr.e1);
   }
+  // one extra record of kind 2: device time from the start of the first recorded launch to the end of the last one (on one stream:
+  // the launches plus every gap between them -- waits for transfers, events, launch latency)
+  int64_t extra = 0;
+  if (n > 0 && records && n < max_records) {
+    float span = 0.f;
+    if (cudaEventElapsedTime(&span, h->prof.front().e0, h->prof.back().e1) == cudaSuccess) {
+      records[3 * n] = 2; records[3 * n + 1] = 0.0; records[3 * n + 2] = span;
+      extra = 1;
+    }
+  }
+  for (auto& pr : h->prof) { h->prof_pool.push_back(pr.e0); h->prof_pool.push_back(pr.e1); }
   h->prof.clear();
-  return n;
+  return n + extra;
 }
 
 int64_t nla_launch_count(nla_handle_t h, int reset) {

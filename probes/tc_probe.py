@@ -88,6 +88,7 @@ def child(group):
         prof = h.profile_read(); h.set_option("profile", 0)
         agg = {}
         for k, f, ms in prof:
+            if k == 2: continue   # span record
             key = ("gemm" if k == 1 else "leaf", f)
             c = agg.setdefault(key, [0, 0.0]); c[0] += 1; c[1] += ms
         rows = [{"kind": k, "gflop_each": round(f * 1e-9, 1), "count": c, "ms_total": round(ms, 3), "tflops": round(f * c / ms * 1e-9, 1)} for (k, f), (c, ms) in sorted(agg.items(), key=lambda kv: -kv[0][1])]

@@ -106,6 +106,16 @@ for (fname, func) in ((:trsm, 'S'), (:trmm, 'M'))
     end
 end
 
+# laswp(A, first, last, ipiv, incx) (src/lu.jl:470-530) on a device matrix; `ipiv` is a CuVector{Int64} (1-based, like the reference).
+# With trsm('L','L','N','U', ...) and GEMM_SUB! above this is every O(n^3) step of one level of getrf2! (src/lu.jl:274-280) on the device.
+function NextLA.laswp(A::StridedCuMatrix{T}, first::Integer, last::Integer, ipiv::CuVector{Int64}, incx::Integer) where {T<:B200Float}
+    GC.@preserve A ipiv check(ccall((:nla_laswp, libnextla), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, CuPtr{Cvoid}, Int64, Int64, Int64, CuPtr{Int64}, Cint, Ptr{Cvoid}),
+        handle(), dtype_code(T), size(A, 1), size(A, 2), pointer(A), max(1, stride(A, 2)), Int64(first), Int64(last), pointer(ipiv), Cint(incx),
+        CUDA.stream().handle))
+    return A
+end
+
 """
     unified_rectrxm_gated!(side, uplo, transpose, alpha, func, A, B, panel_cols, events)
 

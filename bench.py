@@ -108,6 +108,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "TORCHELASTIC_RUN_ID" in os.environ or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun silently exports OMP_NUM_THREADS=1 to every rank; this arm is the reference's CPU path "with all the host threads it can
+        # use", and only rank 0 runs it: give it the cores of the box back (must happen before the OpenMP runtime of the oracle loads)
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     n = m = 2048  # bounded sample: 1/512 of the flops of the headline workload per step
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_port_time(n, m)

@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for ck in 512 1024 2048 4096 0; do
-  timeout 200 python probes/sweep_variants.py --n 16384 --m 16384 --dtypes float32 --cases LUTM,LLNS --opt tc_chunk_k=$ck 2>&1 | sed "s/^/chunk_k=$ck /"
-done | tee gpurun_out/sweep_chunk.txt
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29601"
+timeout 600 $TR bench.py --gpus 2 --steps 5 --warmup 3 2> gpurun_out/bench2.err | tee gpurun_out/bench_2gpu_final.json | cut -c1-200
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/bench_2gpu_final.json') if l.startswith('{')][0]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['e2e']['h2d_bytes_per_step'])"
+timeout 120 $TR bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | cut -c1-200

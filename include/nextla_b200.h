@@ -125,6 +125,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *                 wider type) so that a leaf is ONE triangular tcgen05 GEMM: 0 = default (1024), 128 = plain 128-wide leaves, powers of two up to 4096
  *   "right_via_left" Float64, side 'R': 1 (default) = run the equivalent left-side problem (same Teff) on a transposed copy of B in the handle's
  *                 workspace (n*m*8 bytes, at most 8 GiB) so that the fused slab kernel applies; 0 = the native right-side schedule
+ *   "host_slabs"  host-buffer entry points, Float64: number of independent RHS slabs, each on its own compute stream with its own part of every
+ *                 chunk of B (0 = automatic: one per 4096 vectors, at most 4; 1 = one stream)
  *   "tc_wide_k"   Float16: updates with K >= this value run on 256 x 512 pair tiles (persistent, two accumulators share the A tile: a third
  *                 less L2 traffic per flop); default 4096, 0 = never
  *   "tc_persist"  Float16: 1 (default) = the persistent CTA-pair kernel (static tile list per cluster, two TMEM accumulators, 8 drain warps)

@@ -58,6 +58,7 @@ struct nla_context {
   void* inv_acc; size_t inv_acc_bytes;     // block inverses / phase-1 products in the accumulation type (tri_inv.cuh)
   void* inv_u; size_t inv_u_bytes;
   int64_t pdl;
+  int64_t host_slabs;   // host-buffer pipeline, Float64: RHS slabs on concurrent compute streams (0 = automatic: up to 4, 1 = one)
   int64_t tc_wide_k;    // Float16: updates with K >= this run on 256 x 512 pair tiles (gemm_tc4.cuh); 0 = never
   int64_t right_via_left;   // FP64 right side: 1 = solve the transposed (left-side) problem on a transposed copy of B
   int64_t tc_persist;   // Float16: 1 = persistent CTA-pair kernel (gemm_tc3.cuh) for every multi-tile launch
@@ -1119,7 +1120,7 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
   ctx->diag_ws = nullptr; ctx->diag_ws_bytes = 0;
   ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0; ctx->trmm_batched = 1; ctx->pdl = 1; ctx->tc_dbg = 0;
-  ctx->tc_wide_k = 4096; ctx->right_via_left = 1; ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
+  ctx->host_slabs = 0; ctx->tc_wide_k = 4096; ctx->right_via_left = 1; ctx->tc_persist = 1; ctx->inv_overlap = 1; ctx->prep_stream = nullptr; ctx->prep_event = nullptr;
   ctx->inv_dup = 1; ctx->inv_block = 0; ctx->inv_acc = ctx->inv_u = nullptr; ctx->inv_acc_bytes = ctx->inv_u_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
@@ -1174,6 +1175,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "inv_dup")) { h->inv_dup = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_overlap")) { h->inv_overlap = value != 0; return NLA_OK; }
   if (!strcmp(key, "right_via_left")) { h->right_via_left = value != 0; return NLA_OK; }
+  if (!strcmp(key, "host_slabs")) { if (value < 0 || value > 8) return NLA_ERR_INVALID_DIM; h->host_slabs = value; return NLA_OK; }
   if (!strcmp(key, "tc_wide_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_wide_k = value; return NLA_OK; }
   if (!strcmp(key, "tc_persist")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_persist = value; return NLA_OK; }
   if (!strcmp(key, "inv_block")) {
@@ -1205,6 +1207,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "tc_persist")) return h->tc_persist;
   if (!strcmp(key, "right_via_left")) return h->right_via_left;
   if (!strcmp(key, "tc_wide_k")) return h->tc_wide_k;
+  if (!strcmp(key, "host_slabs")) return h->host_slabs;
   return -1;
 }
 
@@ -1458,12 +1461,17 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   D.A = A_dev ? A_dev : h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
   D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
   Plan plan;
+  // Float64: fused-slab blocks of at most 1024 here (2048 on device-resident data): the first leaf can start after one chunk of B and the
+  // last download is one chunk (measured on C2 with 4 slabs: 142.3 -> 140.9 ms)
+  const int64_t macro_saved = h->macro;
+  if (h->macro > 1024) h->macro = 1024;
   switch (dtype) {
     // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived)
     case NLA_F64: rc = make_plan<double>(h, D, plan, false); break;
     case NLA_F32: rc = make_plan<float>(h, D, plan, false); break;
     default: rc = make_plan<__half>(h, D, plan, false); break;
   }
+  h->macro = macro_saved;
   if (rc != NLA_OK) return rc;
   plan.maps.prep_per_leaf = plan.maps.tc;
   // Large updates are cut along their output range into 1024-wide pieces: a piece needs only its own rows of B and its
@@ -1480,13 +1488,34 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
     }
   }
 
+  // ---- RHS slabs ----
+  // Float64: the right-hand sides are processed in up to 4 independent slabs of vectors, each on its own compute stream, exactly like
+  // the device-resident path: the fused slab leaves (one CTA per 128 vectors) of one slab overlap the updates of another, the first
+  // leaf only has to wait for ITS slab's part of the first chunks of B, and the last download is a quarter of a chunk.
+  // (The tensor-core paths fill the machine from one stream and share per-handle workspaces between ops: one slab.)
+  int64_t S = 1;
+  if (dtype == NLA_F64 && !plan.maps.tc && h->host_slabs != 1) S = std::min<int64_t>(h->host_slabs > 1 ? h->host_slabs : 4, std::max<int64_t>(1, m / 4096));
+  const int64_t per = ((m + S - 1) / S + 127) / 128 * 128;
+  std::vector<int64_t> sv0, snv;
+  for (int64_t q = 0; q < S; q++) {
+    const int64_t v0 = q * per, nv = std::min(per, m - v0);
+    if (nv > 0) { sv0.push_back(v0); snv.push_back(nv); }
+  }
+  S = (int64_t)sv0.size();
+  std::vector<cudaStream_t> cmp((size_t)S, s_cmp);
+  if (S > 1) {
+    int erc = ensure_streams(h, S);
+    if (erc != NLA_OK) return erc;
+    for (int64_t q = 0; q < S; q++) cmp[(size_t)q] = h->streams[(size_t)q];
+  }
+
   // ---- transfer plan ----
   const int64_t nt = (n + TS - 1) / TS;
   const bool a_lower = (uplo == 'L');
-  struct Xfer { int kind; int64_t i, j; };          // kind 0: tile (i,j) of A, kind 1: chunk i of B
+  struct Xfer { int kind; int64_t i, j; };          // kind 0: tile (i,j) of A, kind 1: chunk i of B for slab j
   std::vector<Xfer> xfers;
-  std::vector<int> a_order((size_t)(nt * nt), -1), b_order((size_t)nt, -1), b_last((size_t)nt, -1);
-  std::vector<int> need(ops.size(), -1);
+  std::vector<int> a_order((size_t)(nt * nt), -1), b_order((size_t)(nt * S), -1), b_last((size_t)nt, -1);
+  std::vector<int> need(ops.size() * (size_t)S, -1);
   for (size_t oi = 0; oi < ops.size(); oi++) {
     const Op& o = ops[oi];
     int64_t r0, r1, c0, c1, e0a, e1a, e0b = 0, e1b = 0, w0, w1;
@@ -1497,37 +1526,40 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
       if (P.teff_trans) { r0 = kr0; r1 = kr1; c0 = cr0; c1 = cr1; } else { r0 = cr0; r1 = cr1; c0 = kr0; c1 = kr1; }
       e0a = cr0; e1a = cr1; e0b = kr0; e1b = kr1; w0 = cr0; w1 = cr1;
     }
-    int nd = -1;
-    for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
-      for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
-        if (A_dev) continue;                             // A is not staged by this call
-        if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
-        int& ord = a_order[(size_t)(ti * nt + tj)];
-        if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
-        nd = std::max(nd, ord);
-      }
-    auto touch_b = [&](int64_t e0, int64_t e1) {
-      for (int64_t c = e0 / TS; e1 > e0 && c <= (e1 - 1) / TS; c++) {
-        int& ord = b_order[(size_t)c];
-        if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({1, c, 0}); }
-        nd = std::max(nd, ord);
-      }
-    };
-    touch_b(e0a, e1a);
-    touch_b(e0b, e1b);
-    need[oi] = nd;
+    for (int64_t q = 0; q < S; q++) {
+      int nd = -1;
+      for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
+        for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
+          if (A_dev) continue;                             // A is not staged by this call
+          if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
+          int& ord = a_order[(size_t)(ti * nt + tj)];
+          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
+          nd = std::max(nd, ord);
+        }
+      auto touch_b = [&](int64_t e0, int64_t e1) {
+        for (int64_t c = e0 / TS; e1 > e0 && c <= (e1 - 1) / TS; c++) {
+          int& ord = b_order[(size_t)(c * S + q)];
+          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({1, c, q}); }
+          nd = std::max(nd, ord);
+        }
+      };
+      touch_b(e0a, e1a);
+      touch_b(e0b, e1b);
+      need[oi * (size_t)S + (size_t)q] = nd;
+    }
     for (int64_t c = w0 / TS; c <= (w1 - 1) / TS; c++) b_last[(size_t)c] = (int)oi;
   }
 
-  std::vector<cudaEvent_t> in_ev(xfers.size()), out_ev((size_t)nt);
+  std::vector<cudaEvent_t> in_ev(xfers.size()), out_ev((size_t)(nt * S));
   for (auto& e : in_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : out_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
-  auto b_chunk_copy = [&](int64_t c, bool in, cudaStream_t st) -> cudaError_t {
-    const int64_t e0 = c * TS, ne = std::min(TS, n - e0);
-    char* dptr = (char*)h->stage_b + (P.right ? (size_t)e0 * dldb : (size_t)e0) * es;
-    char* hptr = (char*)B_host + (P.right ? (size_t)e0 * ldb : (size_t)e0) * es;
-    const size_t width = (size_t)(P.right ? m : ne) * es, height = (size_t)(P.right ? ne : m);
+  // chunk c (1024 vector elements) of slab q: rows [e0, e0+ne) x columns [v0, v0+nv) of B (side 'L'), transposed roles for side 'R'
+  auto b_chunk_copy = [&](int64_t c, int64_t q, bool in, cudaStream_t st) -> cudaError_t {
+    const int64_t e0 = c * TS, ne = std::min(TS, n - e0), v0 = sv0[(size_t)q], nv = snv[(size_t)q];
+    char* dptr = (char*)h->stage_b + (P.right ? (size_t)e0 * dldb + (size_t)v0 : (size_t)e0 + (size_t)v0 * dldb) * es;
+    char* hptr = (char*)B_host + (P.right ? (size_t)e0 * ldb + (size_t)v0 : (size_t)e0 + (size_t)v0 * ldb) * es;
+    const size_t width = (size_t)(P.right ? nv : ne) * es, height = (size_t)(P.right ? ne : nv);
     return in ? cudaMemcpy2DAsync(dptr, (size_t)dldb * es, hptr, (size_t)ldb * es, width, height, cudaMemcpyHostToDevice, st)
               : cudaMemcpy2DAsync(hptr, (size_t)ldb * es, dptr, (size_t)dldb * es, width, height, cudaMemcpyDeviceToHost, st);
   };
@@ -1539,40 +1571,46 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
                                     (const char*)A_host + ((size_t)c0 * lda + r0) * es, (size_t)lda * es, (size_t)nr * es, (size_t)nc,
                                     cudaMemcpyHostToDevice, s_in));
     } else {
-      NLA_CUDA(h, b_chunk_copy(xf.i, true, s_in));
+      NLA_CUDA(h, b_chunk_copy(xf.i, xf.j, true, s_in));
     }
     NLA_CUDA(h, cudaEventRecord(in_ev[x], s_in));
   }
 
   // ---- compute + copy-out ----
-  int waited = -1;
-  std::vector<char> gate_waited(gate ? (size_t)gate->n_panels : 0, 0);
+  std::vector<int> waited((size_t)S, -1);
+  std::vector<std::vector<char>> gate_waited((size_t)S, std::vector<char>(gate ? (size_t)gate->n_panels : 0, 0));
   for (size_t oi = 0; oi < ops.size(); oi++) {
-    if (need[oi] > waited) {
-      NLA_CUDA(h, cudaStreamWaitEvent(s_cmp, in_ev[(size_t)need[oi]], 0));
-      waited = need[oi];
-    }
-    if (gate) {
-      int64_t gc0, gc1;
-      op_columns(D, ops[oi], gc0, gc1);
-      if ((rc = gate_wait(h, gate, gate_waited, gc0, gc1, s_cmp)) != NLA_OK) return rc;
-    }
+    int64_t first_last = -1;   // first chunk whose last writer is this op (its out_ev slots serve the op)
+    for (int64_t c = 0; c < nt && first_last < 0; c++) if (b_last[(size_t)c] == (int)oi) first_last = c;
     std::vector<Op> one(1, ops[oi]);
-    switch (dtype) {
-      case NLA_F64: rc = run_ops<double>(h, D, plan.maps, one, 0, m, s_cmp); break;
-      case NLA_F32: rc = run_ops<float>(h, D, plan.maps, one, 0, m, s_cmp); break;
-      default: rc = run_ops<__half>(h, D, plan.maps, one, 0, m, s_cmp); break;
-    }
-    if (rc != NLA_OK) return rc;
-    bool any = false;
-    for (int64_t c = 0; c < nt; c++) any = any || (b_last[(size_t)c] == (int)oi);
-    if (any) {
-      NLA_CUDA(h, cudaEventRecord(out_ev[oi % (size_t)nt], s_cmp));
-      NLA_CUDA(h, cudaStreamWaitEvent(s_out, out_ev[oi % (size_t)nt], 0));
-      for (int64_t c = 0; c < nt; c++)
-        if (b_last[(size_t)c] == (int)oi) NLA_CUDA(h, b_chunk_copy(c, false, s_out));
+    for (int64_t q = 0; q < S; q++) {
+      cudaStream_t cs = cmp[(size_t)q];
+      const int nd = need[oi * (size_t)S + (size_t)q];
+      if (nd > waited[(size_t)q]) {
+        NLA_CUDA(h, cudaStreamWaitEvent(cs, in_ev[(size_t)nd], 0));
+        waited[(size_t)q] = nd;
+      }
+      if (gate) {
+        int64_t gc0, gc1;
+        op_columns(D, ops[oi], gc0, gc1);
+        if ((rc = gate_wait(h, gate, gate_waited[(size_t)q], gc0, gc1, cs)) != NLA_OK) return rc;
+      }
+      switch (dtype) {
+        case NLA_F64: rc = run_ops<double>(h, D, plan.maps, one, sv0[(size_t)q], snv[(size_t)q], cs); break;
+        case NLA_F32: rc = run_ops<float>(h, D, plan.maps, one, sv0[(size_t)q], snv[(size_t)q], cs); break;
+        default: rc = run_ops<__half>(h, D, plan.maps, one, sv0[(size_t)q], snv[(size_t)q], cs); break;
+      }
+      if (rc != NLA_OK) return rc;
+      if (first_last >= 0) {
+        cudaEvent_t oe = out_ev[(size_t)(first_last * S + q)];
+        NLA_CUDA(h, cudaEventRecord(oe, cs));
+        NLA_CUDA(h, cudaStreamWaitEvent(s_out, oe, 0));
+        for (int64_t c = first_last; c < nt; c++)
+          if (b_last[(size_t)c] == (int)oi) NLA_CUDA(h, b_chunk_copy(c, q, false, s_out));
+      }
     }
   }
+  for (int64_t q = 0; q < S; q++) NLA_CUDA(h, cudaStreamSynchronize(cmp[(size_t)q]));
   NLA_CUDA(h, cudaStreamSynchronize(s_out));
   NLA_CUDA(h, cudaStreamSynchronize(s_cmp));
   NLA_CUDA(h, cudaStreamSynchronize(s_in));

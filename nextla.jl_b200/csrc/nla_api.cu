@@ -1494,7 +1494,8 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   // leaf only has to wait for ITS slab's part of the first chunks of B, and the last download is a quarter of a chunk.
   // (The tensor-core paths fill the machine from one stream and share per-handle workspaces between ops: one slab.)
   int64_t S = 1;
-  if (dtype == NLA_F64 && !plan.maps.tc && h->host_slabs != 1) S = std::min<int64_t>(h->host_slabs > 1 ? h->host_slabs : 4, std::max<int64_t>(1, m / 4096));
+  if (dtype == NLA_F64 && !plan.maps.tc && h->host_slabs != 1)
+    S = h->host_slabs > 1 ? std::min<int64_t>(h->host_slabs, std::max<int64_t>(1, m / 256)) : std::min<int64_t>(4, std::max<int64_t>(1, m / 4096));
   const int64_t per = ((m + S - 1) / S + 127) / 128 * 128;
   std::vector<int64_t> sv0, snv;
   for (int64_t q = 0; q < S; q++) {

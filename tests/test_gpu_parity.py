@@ -248,11 +248,16 @@ def test_host_buffer_pipeline_multi_slab(nla, gpu, side, uplo, trans, func):
     """Large enough for several RHS slabs and several column chunks of A (copy-in / solve / copy-out overlapped)."""
     n, m = 4096, 6000
     A, B0 = rp.make_inputs(n, m, side, uplo, np.float64, seed=31, recipe="scaled")
-    B = B0.copy(order="F")
-    nla.unified_rectrxm_host(side, uplo, trans, 1.25, func, A, B)
     blas = rp.blas_reference(side, uplo, trans, 1.25, func, A, B0)
-    assert rel(B, blas) < 1e-13
-    assert rp.error_metric(side, uplo, trans, 1.25, func, A, B0, B) < 1e-14
+    for slabs in (0, 3):   # automatic (one slab at this m) and three RHS slabs on concurrent compute streams, ragged last slab
+        gpu.set_option("host_slabs", slabs)
+        try:
+            B = B0.copy(order="F")
+            nla.unified_rectrxm_host(side, uplo, trans, 1.25, func, A, B, handle=gpu)
+        finally:
+            gpu.set_option("host_slabs", 0)
+        assert rel(B, blas) < 1e-13, slabs
+        assert rp.error_metric(side, uplo, trans, 1.25, func, A, B0, B) < 1e-14, slabs
 
 
 def _gpu_backward_error(torch, side, uplo, trans, alpha, func, dA, dB0, dX):

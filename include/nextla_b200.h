@@ -145,6 +145,16 @@ int64_t nla_get_option(nla_handle_t handle, const char *key);
  * Returns the number of ops (may exceed max_ops) or a negative nla_status.  Needs no GPU. */
 int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t *ops, int64_t max_ops);
 
+/* Host-only introspection of the host-buffer pipeline (nla_rectrxm_host / nla_rectrxm_hostb_gated): the schedule with recursion cutoff
+ * `cutoff`, its large updates cut into 1024-wide pieces, for `slabs` RHS slabs, and the transfer plan that feeds it.  Writes up to
+ * max_ops op records (6 int64 as in nla_plan), up to max_xfers transfer records of 3 int64 {kind (0 = 1024 x 1024 tile (i, j) of A, 1 = chunk i
+ * of 1024 vector elements of B for slab j), i, j} in issue order, *n_xfers = number of transfers, need_out[op * slabs + slab] = index of the
+ * last transfer that op needs for that slab (-1 = none), last_out[chunk] = index of the last op that writes the chunk (its download
+ * follows that op).  a_resident = 1: A is not staged (nla_rectrxm_hostb_gated).  Returns the number of ops or a negative nla_status. */
+int64_t nla_host_plan(char side, char uplo, char trans, char func, int64_t n, int64_t cutoff, int64_t slabs, int a_resident,
+                      int64_t *ops_out, int64_t max_ops, int64_t *xfers_out, int64_t max_xfers, int64_t *n_xfers, int64_t *need_out,
+                      int64_t *last_out);
+
 /* Per-launch device times recorded while option "profile" is 1: waits for the recorded work, writes up to max_records
  * records of 3 doubles {kind (0 = leaf, 1 = GEMM update), algorithmic flops of the launch, milliseconds} in launch order,
  * clears the log and returns the number of records that were available (or a negative nla_status).  If there is room, one more record

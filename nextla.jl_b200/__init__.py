@@ -71,6 +71,8 @@ def load_library():
         "nla_launch_count": (L, [H, I]),
         "nla_profile_read": (L, [H, c.POINTER(c.c_double), L]),
         "nla_plan": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
+        "nla_host_plan": (L, [CH, CH, CH, CH, L, L, L, I, c.POINTER(c.c_int64), L, c.POINTER(c.c_int64), L, c.POINTER(c.c_int64),
+                              c.POINTER(c.c_int64), c.POINTER(c.c_int64)]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -81,7 +83,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp",
+            "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
 
@@ -405,6 +407,26 @@ def lauum(uplo: str, A, ib: int = 1024, **kw):
                 GEMM_ADD(A[i0:i1, i1:], A[i0:i1, i1:], tmp, transb="T", **kw)               # rank-k update                (:127-131)
         Aii.copy_(tri(tmp) + anti(Aii, 1 if lower else -1))
     return A
+
+
+def host_plan(side: str, uplo: str, transpose: str, func: str, n: int, cutoff: int = 1024, slabs: int = 1, a_resident: bool = False):
+    """Host-only: the host-buffer pipeline's plan -- (ops, xfers, need, last): ops as in plan() with the large updates cut into 1024-wide
+    pieces, xfers = [(kind, i, j)] host->device copies in issue order (kind 0: tile (i, j) of A, 1: chunk i of B for slab j),
+    need[op][slab] = index of the last transfer the op waits for, last[chunk] = the op after which the chunk is downloaded."""
+    lib = load_library()
+    nx = ctypes.c_int64(0)
+    args = (_ch(side), _ch(uplo), _ch(transpose), _ch(func), n, cutoff, slabs, 1 if a_resident else 0)
+    nops = lib.nla_host_plan(*args, None, 0, None, 0, ctypes.byref(nx), None, None)
+    if nops < 0:
+        _check(-nops)
+    nt = -(-n // 1024)
+    ops = (ctypes.c_int64 * (6 * max(nops, 1)))()
+    xf = (ctypes.c_int64 * (3 * max(nx.value, 1)))()
+    need = (ctypes.c_int64 * (max(nops, 1) * slabs))()
+    last = (ctypes.c_int64 * max(nt, 1))()
+    lib.nla_host_plan(*args, ops, nops, xf, nx.value, ctypes.byref(nx), need, last)
+    return ([tuple(ops[6 * i + j] for j in range(6)) for i in range(nops)], [tuple(xf[3 * i + j] for j in range(3)) for i in range(nx.value)],
+            [[need[i * slabs + q] for q in range(slabs)] for i in range(nops)], [last[c] for c in range(nt)])
 
 
 def plan(side: str, uplo: str, transpose: str, func: str, n: int, leaf: int = 0):

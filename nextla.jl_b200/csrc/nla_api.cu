@@ -1429,6 +1429,70 @@ int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t
 // copy-in stream in the order the schedule FIRST touches them; every op waits only for the last tile/chunk it needs, and a
 // chunk of B is copied back as soon as the last op that writes it has run.  For C2 this hides all but the first ~5 ms of
 // the 3 GiB of input and the last chunk of output behind the solve.
+// The transfer plan of the host-buffer pipeline, kept apart from the CUDA calls so that it can be checked without a GPU (nla_host_plan).
+struct HostXfer { int kind; int64_t i, j; };   // kind 0: tile (i,j) of A (TS x TS), kind 1: chunk i (TS vector elements) of B for slab j
+struct HostPlan {
+  int64_t TS, nt, S;
+  std::vector<Op> ops;            // the schedule with the large updates cut along their output range into TS-wide pieces: a piece needs only
+                                  // its own rows of B and its own row of tiles of A, so it does not wait for (almost) all of the input
+  std::vector<HostXfer> xfers;    // host -> device copies in issue order: first touch by the schedule, slab by slab within an op
+  std::vector<int> need;          // [op * S + slab]: index of the last transfer that op needs for that slab (-1: none)
+  std::vector<int> b_last;        // [chunk]: the last op that writes the chunk; its download is queued right after that op
+};
+
+static void build_host_plan(bool teff_trans, bool a_lower, bool a_resident, const std::vector<Op>& sched, int64_t n, int64_t S, HostPlan& hp) {
+  const int64_t TS = 1024;
+  hp.TS = TS; hp.S = S; hp.nt = (n + TS - 1) / TS;
+  const int64_t nt = hp.nt;
+  std::vector<Op>& ops = hp.ops;
+  for (const Op& o : sched) {
+    if (o.kind != Op::GEMM || o.cn <= TS) { ops.push_back(o); continue; }
+    for (int64_t c = o.c0; c < o.c0 + o.cn;) {
+      const int64_t cend = std::min(o.c0 + o.cn, (c / TS + 1) * TS);
+      Op piece = o; piece.c0 = c; piece.cn = cend - c;
+      ops.push_back(piece);
+      c = cend;
+    }
+  }
+  std::vector<HostXfer>& xfers = hp.xfers;
+  std::vector<int> a_order((size_t)(nt * nt), -1), b_order((size_t)(nt * S), -1);
+  hp.b_last.assign((size_t)nt, -1);
+  hp.need.assign(ops.size() * (size_t)S, -1);
+  for (size_t oi = 0; oi < ops.size(); oi++) {
+    const Op& o = ops[oi];
+    int64_t r0, r1, c0, c1, e0a, e1a, e0b = 0, e1b = 0, w0, w1;
+    if (o.kind == Op::LEAF) {
+      r0 = c0 = o.off; r1 = c1 = o.off + o.sz; e0a = o.off; e1a = o.off + o.sz; w0 = e0a; w1 = e1a;
+    } else {
+      const int64_t cr0 = o.c0, cr1 = o.c0 + o.cn, kr0 = o.k0, kr1 = o.k0 + o.kn;
+      if (teff_trans) { r0 = kr0; r1 = kr1; c0 = cr0; c1 = cr1; } else { r0 = cr0; r1 = cr1; c0 = kr0; c1 = kr1; }
+      e0a = cr0; e1a = cr1; e0b = kr0; e1b = kr1; w0 = cr0; w1 = cr1;
+    }
+    for (int64_t q = 0; q < S; q++) {
+      int nd = -1;
+      for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
+        for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
+          if (a_resident) continue;                        // A is not staged by this call
+          if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
+          int& ord = a_order[(size_t)(ti * nt + tj)];
+          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
+          nd = std::max(nd, ord);
+        }
+      auto touch_b = [&](int64_t e0, int64_t e1) {
+        for (int64_t c = e0 / TS; e1 > e0 && c <= (e1 - 1) / TS; c++) {
+          int& ord = b_order[(size_t)(c * S + q)];
+          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({1, c, q}); }
+          nd = std::max(nd, ord);
+        }
+      };
+      touch_b(e0a, e1a);
+      touch_b(e0b, e1b);
+      hp.need[oi * (size_t)S + (size_t)q] = nd;
+    }
+    for (int64_t c = w0 / TS; c <= (w1 - 1) / TS; c++) hp.b_last[(size_t)c] = (int)oi;
+  }
+}
+
 // `A_dev` != nullptr: A is (or is becoming, see `gate`) resident on the device with leading dimension `lda_dev`; only B is staged.
 static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                          const void* A_host, int64_t lda, void* B_host, int64_t ldb, const void* A_dev, int64_t lda_dev, const Gate* gate) {
@@ -1474,20 +1538,6 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   h->macro = macro_saved;
   if (rc != NLA_OK) return rc;
   plan.maps.prep_per_leaf = plan.maps.tc;
-  // Large updates are cut along their output range into 1024-wide pieces: a piece needs only its own rows of B and its
-  // own row of tiles of A, so the top-level update no longer has to wait for (almost) all of the input to arrive.
-  const int64_t TS = 1024;
-  std::vector<Op> ops;
-  for (const Op& o : plan.ops) {
-    if (o.kind != Op::GEMM || o.cn <= TS) { ops.push_back(o); continue; }
-    for (int64_t c = o.c0; c < o.c0 + o.cn;) {
-      const int64_t cend = std::min(o.c0 + o.cn, (c / TS + 1) * TS);
-      Op piece = o; piece.c0 = c; piece.cn = cend - c;
-      ops.push_back(piece);
-      c = cend;
-    }
-  }
-
   // ---- RHS slabs ----
   // Float64: the right-hand sides are processed in up to 4 independent slabs of vectors, each on its own compute stream, exactly like
   // the device-resident path: the fused slab leaves (one CTA per 128 vectors) of one slab overlap the updates of another, the first
@@ -1510,46 +1560,14 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
     for (int64_t q = 0; q < S; q++) cmp[(size_t)q] = h->streams[(size_t)q];
   }
 
-  // ---- transfer plan ----
-  const int64_t nt = (n + TS - 1) / TS;
-  const bool a_lower = (uplo == 'L');
-  struct Xfer { int kind; int64_t i, j; };          // kind 0: tile (i,j) of A, kind 1: chunk i of B for slab j
-  std::vector<Xfer> xfers;
-  std::vector<int> a_order((size_t)(nt * nt), -1), b_order((size_t)(nt * S), -1), b_last((size_t)nt, -1);
-  std::vector<int> need(ops.size() * (size_t)S, -1);
-  for (size_t oi = 0; oi < ops.size(); oi++) {
-    const Op& o = ops[oi];
-    int64_t r0, r1, c0, c1, e0a, e1a, e0b = 0, e1b = 0, w0, w1;
-    if (o.kind == Op::LEAF) {
-      r0 = c0 = o.off; r1 = c1 = o.off + o.sz; e0a = o.off; e1a = o.off + o.sz; w0 = e0a; w1 = e1a;
-    } else {
-      const int64_t cr0 = o.c0, cr1 = o.c0 + o.cn, kr0 = o.k0, kr1 = o.k0 + o.kn;
-      if (P.teff_trans) { r0 = kr0; r1 = kr1; c0 = cr0; c1 = cr1; } else { r0 = cr0; r1 = cr1; c0 = kr0; c1 = kr1; }
-      e0a = cr0; e1a = cr1; e0b = kr0; e1b = kr1; w0 = cr0; w1 = cr1;
-    }
-    for (int64_t q = 0; q < S; q++) {
-      int nd = -1;
-      for (int64_t tj = c0 / TS; tj <= (c1 - 1) / TS; tj++)
-        for (int64_t ti = r0 / TS; ti <= (r1 - 1) / TS; ti++) {
-          if (A_dev) continue;                             // A is not staged by this call
-          if (a_lower ? (ti < tj) : (ti > tj)) continue;   // tile entirely in the unreferenced triangle
-          int& ord = a_order[(size_t)(ti * nt + tj)];
-          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({0, ti, tj}); }
-          nd = std::max(nd, ord);
-        }
-      auto touch_b = [&](int64_t e0, int64_t e1) {
-        for (int64_t c = e0 / TS; e1 > e0 && c <= (e1 - 1) / TS; c++) {
-          int& ord = b_order[(size_t)(c * S + q)];
-          if (ord < 0) { ord = (int)xfers.size(); xfers.push_back({1, c, q}); }
-          nd = std::max(nd, ord);
-        }
-      };
-      touch_b(e0a, e1a);
-      touch_b(e0b, e1b);
-      need[oi * (size_t)S + (size_t)q] = nd;
-    }
-    for (int64_t c = w0 / TS; c <= (w1 - 1) / TS; c++) b_last[(size_t)c] = (int)oi;
-  }
+  // ---- transfer plan (host-only logic: build_host_plan, inspectable through nla_host_plan) ----
+  HostPlan hp;
+  build_host_plan(P.teff_trans, uplo == 'L', A_dev != nullptr, plan.ops, n, S, hp);
+  const int64_t TS = hp.TS, nt = hp.nt;
+  const std::vector<Op>& ops = hp.ops;
+  const std::vector<HostXfer>& xfers = hp.xfers;
+  const std::vector<int>& need = hp.need;
+  const std::vector<int>& b_last = hp.b_last;
 
   std::vector<cudaEvent_t> in_ev(xfers.size()), out_ev((size_t)(nt * S));
   for (auto& e : in_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1565,7 +1583,7 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
               : cudaMemcpy2DAsync(hptr, (size_t)ldb * es, dptr, (size_t)dldb * es, width, height, cudaMemcpyDeviceToHost, st);
   };
   for (size_t x = 0; x < xfers.size(); x++) {
-    const Xfer& xf = xfers[x];
+    const HostXfer& xf = xfers[x];
     if (xf.kind == 0) {
       const int64_t r0 = xf.i * TS, c0 = xf.j * TS, nr = std::min(TS, n - r0), nc = std::min(TS, n - c0);
       NLA_CUDA(h, cudaMemcpy2DAsync((char*)h->stage_a + ((size_t)c0 * dlda + r0) * es, (size_t)dlda * es,
@@ -1621,6 +1639,37 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
 }
 
 extern "C" {
+
+int64_t nla_host_plan(char side, char uplo, char trans, char func, int64_t n, int64_t cutoff, int64_t slabs, int a_resident, int64_t* ops_out,
+                      int64_t max_ops, int64_t* xfers_out, int64_t max_xfers, int64_t* n_xfers, int64_t* need_out, int64_t* last_out) {
+  Problem P;
+  int rc = make_problem(P, side, uplo, trans, func, NLA_F64, n, 1, 1.0, (const void*)8, std::max<int64_t>(1, n), (void*)8, std::max<int64_t>(1, n));
+  if (rc != NLA_OK) return -rc;
+  if (slabs < 1 || slabs > 8 || cutoff < 1 || cutoff > 4096) return -NLA_ERR_INVALID_DIM;
+  if (n_xfers) *n_xfers = 0;
+  if (n == 0) return 0;
+  std::vector<Op> sched;
+  build_schedule(P, cutoff, 0, n, false, true, sched);
+  HostPlan hp;
+  build_host_plan(P.teff_trans, uplo == 'L', a_resident != 0, sched, n, slabs, hp);
+  for (size_t i = 0; i < hp.ops.size() && (int64_t)i < max_ops; i++) {
+    const Op& o = hp.ops[i];
+    if (ops_out) {
+      int64_t* r = ops_out + 6 * i;
+      r[0] = o.kind == Op::GEMM;
+      r[1] = o.kind == Op::GEMM ? o.c0 : o.off; r[2] = o.kind == Op::GEMM ? o.cn : o.sz;
+      r[3] = o.kind == Op::GEMM ? o.k0 : 0; r[4] = o.kind == Op::GEMM ? o.kn : 0;
+      r[5] = (o.pre != 1.0) || (o.post != 1.0);
+    }
+    if (need_out) for (int64_t q = 0; q < slabs; q++) need_out[i * (size_t)slabs + (size_t)q] = hp.need[i * (size_t)slabs + (size_t)q];
+  }
+  for (size_t x = 0; x < hp.xfers.size() && (int64_t)x < max_xfers && xfers_out; x++) {
+    xfers_out[3 * x] = hp.xfers[x].kind; xfers_out[3 * x + 1] = hp.xfers[x].i; xfers_out[3 * x + 2] = hp.xfers[x].j;
+  }
+  if (n_xfers) *n_xfers = (int64_t)hp.xfers.size();
+  if (last_out) for (int64_t c = 0; c < hp.nt; c++) last_out[c] = hp.b_last[(size_t)c];
+  return (int64_t)hp.ops.size();
+}
 
 int nla_rectrxm_host(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                      const void* A_host, int64_t lda, void* B_host, int64_t ldb) {

@@ -158,3 +158,64 @@ def test_large_cutoff_schedule_invariants(nla, n, cutoff):
                 assert prev[1] <= cur[1] and cur[1] + cur[2] <= prev[1] + prev[2], (side, uplo, trans, func, prev, cur)
         flops = sum(cn * cn if kind == 0 else 2 * cn * kn for kind, c0, cn, k0, kn, _ in ops)
         assert flops == n * n
+
+
+@pytest.mark.parametrize("n,cutoff,slabs,resident", [(4096, 1024, 1, False), (5000, 1024, 4, False), (16384, 1024, 4, False), (3000, 128, 3, True), (9000, 2048, 2, False)])
+def test_host_pipeline_transfer_plan(nla, n, cutoff, slabs, resident):
+    """The plan behind nla_rectrxm_host (host-only, nla_host_plan), for every side/uplo/trans/func: (1) exactly the 1024 x 1024 tiles of A that
+    touch the referenced triangle are uploaded, once each (none when A is resident), and every (chunk, slab) of B once; (2) no op runs
+    before everything it reads has been queued: its A block and its rows of B -- the rows it writes and, for an update, the rows it
+    multiplies -- have transfer indices <= need[op][slab]; (3) the pieces of a cut update tile its output range; (4) a chunk is downloaded
+    after the last op that writes it and no later op writes it; (5) transfers are issued in first-touch order (need is non-decreasing
+    along the schedule for a slab, and slab q never waits for more than slab q+1 at the same op)."""
+    TS = 1024
+    nt = -(-n // TS)
+    for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+        ops, xfers, need, last = nla.host_plan(side, uplo, trans, func, n, cutoff, slabs, resident)
+        right, tr = side == "R", trans != "N"
+        teff_trans = tr != right
+        lower = uplo == "L"
+        a_idx = {(i, j): x for x, (k, i, j) in enumerate(xfers) if k == 0}
+        b_idx = {(i, j): x for x, (k, i, j) in enumerate(xfers) if k == 1}
+        assert len(a_idx) + len(b_idx) == len(xfers)                                   # (1) nothing twice
+        want_tiles = set() if resident else {(i, j) for i in range(nt) for j in range(nt) if (i >= j if lower else i <= j)}
+        assert set(a_idx) == want_tiles
+        assert set(b_idx) == {(c, q) for c in range(nt) for q in range(slabs)}
+        # (3) the schedule is the plain one with the wide updates cut at multiples of 1024
+        plain = nla.plan(side, uplo, trans, func, n, cutoff)
+        rebuilt, i = [], 0
+        while i < len(ops):
+            kind, c0, cn, k0, kn, _ = ops[i]
+            if kind == 1:
+                j = i
+                while j + 1 < len(ops) and ops[j + 1][0] == 1 and ops[j + 1][3:5] == (k0, kn) and ops[j + 1][1] == ops[j][1] + ops[j][2] and ops[j][2] <= TS and (ops[j][1] + ops[j][2]) % TS == 0:
+                    j += 1
+                rebuilt.append((1, c0, ops[j][1] + ops[j][2] - c0, k0, kn))
+                i = j + 1
+            else:
+                rebuilt.append((0, c0, cn, 0, 0)); i += 1
+        assert rebuilt == [p[:5] for p in plain], (side, uplo, trans, func)
+        writers = {}
+        for oi, (kind, c0, cn, k0, kn, _) in enumerate(ops):
+            rows_b = [(c0, c0 + cn)] + ([(k0, k0 + kn)] if kind == 1 else [])
+            if kind == 0:
+                ar, ac = (c0, c0 + cn), (c0, c0 + cn)
+            else:
+                ar, ac = ((k0, k0 + kn), (c0, c0 + cn)) if teff_trans else ((c0, c0 + cn), (k0, k0 + kn))
+            for q in range(slabs):
+                nd = need[oi][q]
+                for lo, hi in rows_b:                                                     # (2) B rows
+                    for c in range(lo // TS, (hi - 1) // TS + 1):
+                        assert b_idx[(c, q)] <= nd
+                if not resident:                                                          # (2) A block (tiles inside the triangle)
+                    for ti in range(ar[0] // TS, (ar[1] - 1) // TS + 1):
+                        for tj in range(ac[0] // TS, (ac[1] - 1) // TS + 1):
+                            if (ti, tj) in a_idx:
+                                assert a_idx[(ti, tj)] <= nd
+                if oi > 0:
+                    assert need[oi][q] >= -1 and max(need[oi][q], need[oi - 1][q]) >= need[oi - 1][q]
+                if q + 1 < slabs:
+                    assert need[oi][q] <= need[oi][q + 1]                                 # (5) slab order within an op
+            for c in range(c0 // TS, (c0 + cn - 1) // TS + 1):
+                writers[c] = oi
+        assert [writers[c] for c in range(nt)] == last                                    # (4)

@@ -28,17 +28,34 @@ enum nla_status {
   NLA_ERR_CUDA = 5,           /* a CUDA runtime/driver call failed; nla_last_cuda_error() has the code */
   NLA_ERR_NO_DEVICE = 6,
   NLA_ERR_UNSUPPORTED = 7,
-  NLA_ERR_INVALID_HANDLE = 8
+  NLA_ERR_INVALID_HANDLE = 8,
+  NLA_ERR_WORKSPACE = 9,      /* caller-provided workspace (nla_set_workspace) too small even for the degraded schedule */
+  NLA_ERR_NCCL = 10           /* libnccl could not be loaded, or an NCCL call failed (nla_mg_*) */
 };
 
-/* Library lifetime.  One handle per (host thread, device); re-entrant across handles, no global mutable state.
- * A handle owns a small device workspace (prepared diagonal blocks of the Float32/Float16 path): calls through ONE handle must be
- * ordered on one stream (or otherwise serialised); use one handle per concurrently used stream. */
+/* Library lifetime.  One handle per (host thread / task, device, stream); re-entrant across handles, no process-global mutable state
+ * (per-kernel attributes, helper streams and workspaces all live in the handle).  A handle owns device workspaces (prepared diagonal
+ * blocks / block inverses of the Float32/Float16 path, a copy of B for the batched multiply and the Float64 right side): calls through
+ * ONE handle must be ordered on ONE stream -- use one handle per concurrently used stream (the Julia and Python bindings key their
+ * handle cache by (device, stream)).  Every entry point runs on the handle's device and restores the caller's current device. */
 int nla_create(nla_handle_t *handle, int device);
 int nla_destroy(nla_handle_t handle);
 const char *nla_status_string(int status);
 int nla_last_cuda_error(nla_handle_t handle);
 int nla_version(void);
+
+/* Workspace control.  By default the handle's workspaces grow on demand with the STREAM-ORDERED allocator
+ * (cudaMallocAsync on the call's stream): no device synchronisation, the call stays asynchronous even when it has to grow one.
+ *   nla_workspace_bytes  bytes the call (side, func, dtype, n, m) needs under the handle's current options (0 for Float64 left side)
+ *   nla_reserve          pre-size the library-owned workspaces (and create the helper streams) for that call: afterwards calls of that
+ *                        shape or smaller allocate nothing
+ *   nla_set_workspace    use a caller-owned device arena (256-byte aligned) instead: the library then never allocates on the
+ *                        nla_rectrxm / nla_trxm / nla_gemm_update path.  If the arena is smaller than nla_workspace_bytes the call degrades
+ *                        (128-wide leaves instead of block inverses, in-place instead of batched multiply, native instead of transposed
+ *                        right side) and only returns NLA_ERR_WORKSPACE when even that does not fit.  (NULL, 0) returns to library-owned. */
+int64_t nla_workspace_bytes(nla_handle_t handle, char side, char func, int dtype, int64_t n, int64_t m);
+int nla_reserve(nla_handle_t handle, char side, char func, int dtype, int64_t n, int64_t m);
+int nla_set_workspace(nla_handle_t handle, void *workspace, int64_t bytes);
 
 /* unified_rectrxm!(side, uplo, transpose, alpha, func, A, B)            -- src/rectrxm.jl:43-76 (+ unified_rec :101-198)
  *   func 'S': B <- alpha * op(A)^-1 * B (side 'L')  or  alpha * B * op(A)^-1 (side 'R')
@@ -134,7 +151,17 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "inv_dup"     1 (default) = an update also writes the block of B the next block-inverse leaf reads into the leaf's workspace (0: one copy per leaf)
  *   "inv_overlap" 1 (default) = all but the first two block inverses are computed on a side stream while the solve is running
  *   "pdl"         1 (default) = launch the tcgen05 kernels with programmatic dependent launch (prologue overlaps the predecessor's tail)
- *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)  */
+ *   "inv_guard"   Float32/Float16 solve with block inverses: 1 (default) = conditioning guard.  Every inverted block gets a device-side
+ *                 record (||T||_F, ||inv T||_F, non-finite entries); a block whose ||T||_F ||inv T||_F / order exceeds 1/(32 eps) (64 for
+ *                 Float16, 524288 for Float32) or whose rounded inverse is not finite is solved by SUBSTITUTION (the reference's leaf
+ *                 arithmetic, src/trsm.jl:15-27; backward stable for any conditioning) instead of the inverse GEMM.  Decided on the device,
+ *                 the call stays asynchronous.  0 = off: the solve is then only conditionally stable (error ~ eps * cond(block)).
+ *   "inv_guard_kappa" threshold override of the guard (0 = the default above; 1 rejects every block = substitution leaves everywhere)
+ *   "nvtx"        1 = NVTX ranges around every call and schedule op (nsys / ncu --nvtx)
+ *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)
+ * Read-only keys of nla_get_option:
+ *     "inv_fallbacks" (synchronises) number of blocks of the last guarded solve that took the substitution fallback
+ *     "ws_allocs"     device allocations made by the library for this handle so far  */
 int nla_set_option(nla_handle_t handle, const char *key, int64_t value);
 int64_t nla_get_option(nla_handle_t handle, const char *key);
 
@@ -160,6 +187,10 @@ int64_t nla_host_plan(char side, char uplo, char trans, char func, int64_t n, in
  * clears the log and returns the number of records that were available (or a negative nla_status).  If there is room, one more record
  * of kind 2 follows: the device time from the start of the first launch to the end of the last (launches + the gaps between them). */
 int64_t nla_profile_read(nla_handle_t handle, double *records, int64_t max_records);
+
+/* Measured FP64 tensor-core peak of the handle's GPU: runs a DMMA.8x8x4 issue-rate microbenchmark (a few milliseconds, synchronous)
+ * and writes TFLOP/s.  bench.py's FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 figure). */
+int nla_probe_fp64_peak(nla_handle_t handle, double *tflops);
 
 /* Counters for bench.py: kernels launched by this handle since the last reset. */
 int64_t nla_launch_count(nla_handle_t handle, int reset);

@@ -54,6 +54,10 @@ def load_library():
         "nla_status_string": (c.c_char_p, [I]),
         "nla_last_cuda_error": (I, [H]),
         "nla_version": (I, []),
+        "nla_probe_fp64_peak": (I, [H, c.POINTER(c.c_double)]),
+        "nla_workspace_bytes": (L, [H, CH, CH, I, L, L]),
+        "nla_reserve": (I, [H, CH, CH, I, L, L]),
+        "nla_set_workspace": (I, [H, P, L]),
         "nla_rectrxm": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
         "nla_trxm": (I, [H, CH, CH, CH, CH, CH, I, L, L, D, P, L, P, L, P]),
         "nla_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L]),
@@ -83,6 +87,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
+            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak",
             "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
@@ -111,6 +116,30 @@ class Handle:
     def get_option(self, key: str) -> int:
         return int(load_library().nla_get_option(self._h, key.encode()))
 
+    def workspace_bytes(self, side: str, func: str, dtype_code: int, n: int, m: int) -> int:
+        r = int(load_library().nla_workspace_bytes(self._h, side.encode(), func.encode(), dtype_code, n, m))
+        if r < 0:
+            _check(-r, self._h)
+        return r
+
+    def reserve(self, side: str, func: str, dtype_code: int, n: int, m: int):
+        _check(load_library().nla_reserve(self._h, side.encode(), func.encode(), dtype_code, n, m), self._h)
+
+    def set_workspace(self, buf):
+        """Caller-owned arena: a 1-D torch CUDA uint8 tensor (256-byte aligned), or None to return to library-owned workspaces.
+        The tensor is kept alive by the handle."""
+        self._ws_keepalive = buf
+        if buf is None:
+            _check(load_library().nla_set_workspace(self._h, None, 0), self._h)
+        else:
+            _check(load_library().nla_set_workspace(self._h, buf.data_ptr(), buf.numel() * buf.element_size()), self._h)
+
+    def probe_fp64_peak(self) -> float:
+        """Measured DMMA.8x8x4 issue-rate peak of this GPU in TFLOP/s (a few milliseconds, synchronous)."""
+        v = ctypes.c_double(0.0)
+        _check(load_library().nla_probe_fp64_peak(self._h, ctypes.byref(v)), self._h)
+        return float(v.value)
+
     def launch_count(self, reset: bool = False) -> int:
         return int(load_library().nla_launch_count(self._h, 1 if reset else 0))
 
@@ -135,14 +164,27 @@ class Handle:
             pass
 
 
-def default_handle(device: Optional[int] = None) -> Handle:
+def default_handle(device: Optional[int] = None, stream=None) -> Handle:
+    """The cached handle of (device, stream).  A handle owns device workspaces, so calls through one handle must be ordered on one
+    stream (include/nextla_b200.h): the cache is keyed by the stream as well -- two threads / streams on one GPU get two handles."""
     import torch
 
     if device is None:
         device = torch.cuda.current_device()
-    if device not in _handles:
-        _handles[device] = Handle(device)
-    return _handles[device]
+    s = torch.cuda.current_stream(device) if stream is None else stream
+    key = (device, int(s.cuda_stream))
+    if key not in _handles:
+        _handles[key] = Handle(device)
+    return _handles[key]
+
+
+def _handle_for(handle: Optional["Handle"], t, stream=None) -> "Handle":
+    """Explicit handle (checked against the tensor's device) or the cached one of (tensor device, stream)."""
+    if handle is None:
+        return default_handle(t.device.index, stream)
+    if handle.device != t.device.index:
+        raise NextLAError(f"handle of device {handle.device} used with a matrix on device {t.device.index}")
+    return handle
 
 
 # ---- column-major device matrices ---------------------------------------------------------------
@@ -189,10 +231,10 @@ def _desc(t):
     return t.data_ptr(), rows, cols, ld, code
 
 
-def _stream_ptr(stream):
+def _stream_ptr(stream, device=None):
     import torch
 
-    s = torch.cuda.current_stream() if stream is None else stream
+    s = torch.cuda.current_stream(device) if stream is None else stream
     return ctypes.c_void_p(s.cuda_stream)
 
 
@@ -205,7 +247,7 @@ def _ch(c: str) -> bytes:
 def unified_rectrxm(side: str, uplo: str, transpose: str, alpha: float, func: str, A, B, stream=None, handle: Optional[Handle] = None):
     """unified_rectrxm!(side, uplo, transpose, alpha, func, A, B) -- src/rectrxm.jl:43-76.  In place on B; returns B.
     Asynchronous on the current torch stream, like the reference (which does not synchronise, :75)."""
-    h = handle or default_handle(A.device.index)
+    h = _handle_for(handle, A, stream)
     pa, ar, ac, lda, dta = _desc(A)
     pb, br, bc, ldb, dtb = _desc(B)
     if dta != dtb:
@@ -217,7 +259,7 @@ def unified_rectrxm(side: str, uplo: str, transpose: str, alpha: float, func: st
     if (side == "L" and br != n) or (side == "R" and bc != n):
         raise NextLAError("dimension mismatch between A and B")
     rc = load_library().nla_rectrxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
-                                    _stream_ptr(stream))
+                                    _stream_ptr(stream, h.device))
     _check(rc, h._h)
     return B
 
@@ -238,7 +280,7 @@ def unified_rectrxm_gated(side: str, uplo: str, transpose: str, alpha: float, fu
                           handle: Optional[Handle] = None):
     """unified_rectrxm with A arriving in column panels: `panel_events[p]` is a recorded torch.cuda.Event marking panel p
     (columns [p*panel_cols, (p+1)*panel_cols)) valid; the schedule waits for a panel right before the first launch reading it."""
-    h = handle or default_handle(A.device.index)
+    h = _handle_for(handle, A, stream)
     pa, ar, ac, lda, dta = _desc(A)
     pb, br, bc, ldb, dtb = _desc(B)
     if dta != dtb or ar != ac:
@@ -249,7 +291,7 @@ def unified_rectrxm_gated(side: str, uplo: str, transpose: str, alpha: float, fu
         raise NextLAError("dimension mismatch between A and B")
     evs = (ctypes.c_void_p * len(panel_events))(*[ctypes.c_void_p(e.cuda_event) for e in panel_events])
     rc = load_library().nla_rectrxm_gated(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
-                                          _stream_ptr(stream), int(panel_cols), len(panel_events), evs)
+                                          _stream_ptr(stream, h.device), int(panel_cols), len(panel_events), evs)
     _check(rc, h._h)
     return B
 
@@ -268,7 +310,7 @@ def unified_rectrxm_host(side, uplo, transpose, alpha, func, A: np.ndarray, B: n
 
 
 def _leaf(solve: bool, side: str, uplo: str, A, B, stream=None, handle=None):
-    h = handle or default_handle(A.device.index)
+    h = _handle_for(handle, A, stream)
     pa, ar, ac, lda, dta = _desc(A)
     pb, br, bc, ldb, dtb = _desc(B)
     if dta != dtb or ar != ac:
@@ -276,7 +318,7 @@ def _leaf(solve: bool, side: str, uplo: str, A, B, stream=None, handle=None):
     n = ar
     m = bc if side == "L" else br
     fn = load_library().nla_trsm_leaf if solve else load_library().nla_trmm_leaf
-    _check(fn(h._h, _ch(side), _ch(uplo), dta, n, m, pa, lda, pb, ldb, _stream_ptr(stream)), h._h)
+    _check(fn(h._h, _ch(side), _ch(uplo), dta, n, m, pa, lda, pb, ldb, _stream_ptr(stream, h.device)), h._h)
     return B
 
 
@@ -291,14 +333,14 @@ def RightUpperTRMM(A, B, **kw): return _leaf(False, "R", "U", A, B, **kw)    # s
 
 
 def _gemm(C, A, B, sign: int, transa="N", transb="N", stream=None, handle=None):
-    h = handle or default_handle(C.device.index)
+    h = _handle_for(handle, C, stream)
     pa, ar, ac, lda, dta = _desc(A)
     pb, br, bc, ldb, dtb = _desc(B)
     pc, M, N, ldc, dtc = _desc(C)
     K = ac if transa == "N" else ar
     if not (dta == dtb == dtc):
         raise NextLAError("GEMM operands must share one element type")
-    _check(load_library().nla_gemm_update(h._h, dtc, _ch(transa), _ch(transb), M, N, K, sign, pa, lda, pb, ldb, pc, ldc, _stream_ptr(stream)), h._h)
+    _check(load_library().nla_gemm_update(h._h, dtc, _ch(transa), _ch(transb), M, N, K, sign, pa, lda, pb, ldb, pc, ldc, _stream_ptr(stream, h.device)), h._h)
     return C
 
 
@@ -314,7 +356,7 @@ def GEMM_SUB(A, B, C, **kw):
 
 def unified_trxm(side: str, uplo: str, transpose: str, diag: str, alpha: float, func: str, A, B, stream=None, handle: Optional[Handle] = None):
     """unified_rectrxm with the BLAS `diag` flag (nla_trxm): diag = 'U' treats the diagonal of A as ones without reading it."""
-    h = handle or default_handle(A.device.index)
+    h = _handle_for(handle, A, stream)
     pa, ar, ac, lda, dta = _desc(A)
     pb, br, bc, ldb, dtb = _desc(B)
     if dta != dtb or ar != ac:
@@ -324,7 +366,7 @@ def unified_trxm(side: str, uplo: str, transpose: str, diag: str, alpha: float, 
     if (side == "L" and br != n) or (side == "R" and bc != n):
         raise NextLAError("dimension mismatch between A and B")
     rc = load_library().nla_trxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(diag), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
-                                 _stream_ptr(stream))
+                                 _stream_ptr(stream, h.device))
     _check(rc, h._h)
     return B
 
@@ -345,13 +387,13 @@ def laswp(A, first: int, last: int, ipiv, incx: int = 1, stream=None, handle: Op
     `ipiv` is a CUDA int64 vector."""
     import torch
 
-    h = handle or default_handle(A.device.index)
+    h = _handle_for(handle, A, stream)
     pa, rows, cols, lda, dta = _desc(A)
     if not (ipiv.is_cuda and ipiv.dtype == torch.int64 and ipiv.is_contiguous()):
         raise NextLAError("ipiv must be a contiguous CUDA int64 vector")
     if last > ipiv.numel():
         raise NextLAError("ipiv is shorter than `last`")
-    _check(load_library().nla_laswp(h._h, dta, rows, cols, pa, lda, int(first), int(last), ipiv.data_ptr(), int(incx), _stream_ptr(stream)), h._h)
+    _check(load_library().nla_laswp(h._h, dta, rows, cols, pa, lda, int(first), int(last), ipiv.data_ptr(), int(incx), _stream_ptr(stream, h.device)), h._h)
     return A
 
 

@@ -88,7 +88,17 @@ struct GemmTcParams {
   // columns [dup_c0, +dup_cn) are also stored column-major at dup (leading dimension dup_ld)
   void* dup; long long dup_ld;
   int dup_r0, dup_rn, dup_c0, dup_cn;
+  // conditioning guard of a block-inverse leaf (tri_guard.cuh): when the record says the block is ill-conditioned the launch does
+  // nothing and the substitution kernel launched right behind it solves the block instead
+  const double* skip_rec; double skip_thr2;
 };
+
+__device__ __forceinline__ bool tc_skip_launch(const GemmTcParams& p) {
+  if (!p.skip_rec) return false;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the record is written by a predecessor on the stream (or a side stream joined by an event)
+  const double r0 = p.skip_rec[0], r1 = p.skip_rec[1], r2 = p.skip_rec[2];
+  return r2 > 0.0 || !(r0 * r1 <= p.skip_thr2);
+}
 
 // instruction descriptor: FP32 accumulate, A/B format, majorness (0 = K-major, 1 = MN-major), N >> 3, M >> 4
 template <typename T, int AMAJ, int BMAJ, int BN>
@@ -127,6 +137,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (tc_skip_launch(p)) return;   // uniform for the grid; nothing allocated yet
 
   // grouped rasterisation: CTAs resident together share A row panels / B column panels in L2
   const int per_group = TC_GROUP_M * p.tiles_n;

@@ -105,6 +105,8 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
+  if (tc_skip_launch(p)) return;   // uniform for the grid (both CTAs of every pair); nothing allocated, no cluster barrier passed yet
+
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pairs_m = (p.tiles_m + 1) >> 1;

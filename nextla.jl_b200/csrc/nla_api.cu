@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <unordered_set>
 #include <vector>
 
 #include "gemm_f64.cuh"
@@ -18,7 +19,9 @@
 #include "gemm_tc4.cuh"
 #include "diag_prep.cuh"
 #include "tri_inv.cuh"
+#include "tri_guard.cuh"
 #include "laswp.cuh"
+#include "probe.cuh"
 
 using namespace nla;
 
@@ -72,6 +75,17 @@ struct nla_context {
   void* stage_b; size_t stage_b_bytes;
   cudaStream_t host_streams[3];
   cudaEvent_t host_events[8];
+  // kernels whose dynamic shared-memory limit has been raised on this handle's device (cudaFuncSetAttribute is per device and a handle
+  // drives one device from one host thread at a time: no process-global state)
+  std::unordered_set<const void*> attr_done;
+  // caller-provided device workspace (nla_set_workspace): when set, the library allocates nothing on the nla_rectrxm / nla_trxm path
+  void* user_ws; size_t user_ws_bytes;
+  int64_t ws_allocs;    // number of device allocations made by the library on behalf of this handle (tests: must not grow on a warm handle)
+  int64_t inv_guard;    // Float32/Float16 solve: 1 = conditioning guard on the block inverses (see nla_set_option "inv_guard")
+  void* cond_ws; size_t cond_ws_bytes;   // per inverted block: {sum of squares of the block of A, of its inverse, non-finite count, fallback taken}
+  int64_t inv_guard_kappa;   // threshold override of the guard (0 = default per element type)
+  int64_t cond_blocks;       // number of records the last guarded solve wrote (nla_get_option "inv_fallbacks" reads them back)
+  int64_t nvtx;         // 1 = NVTX ranges around calls and schedule ops
 };
 
 static const uint32_t NLA_MAGIC = 0x4e4c4142u;  // "NLAB"
@@ -86,6 +100,30 @@ static const uint32_t NLA_MAGIC = 0x4e4c4142u;  // "NLAB"
   } while (0)
 
 static inline size_t dtype_size(int dtype) { return dtype == NLA_F64 ? 8 : dtype == NLA_F32 ? 4 : 2; }
+
+// Raise a kernel's dynamic shared-memory limit once per handle (= once per device for that handle).
+template <typename F>
+static int ensure_smem_attr(nla_context* ctx, F* func, int bytes) {
+  const void* key = (const void*)func;
+  if (ctx->attr_done.count(key)) return NLA_OK;
+  NLA_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->attr_done.insert(key);
+  return NLA_OK;
+}
+
+// Every entry point runs on the handle's device and gives the caller its current device back (torch / CUDA.jl keep their own notion
+// of the current device; a library call must not change it behind their back).
+struct DeviceGuard {
+  int prev; bool changed; cudaError_t err;
+  explicit DeviceGuard(int dev) : prev(-1), changed(false) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); changed = (err == cudaSuccess); }
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define NLA_ON_DEVICE(h) DeviceGuard dev_guard__((h)->device); NLA_CUDA((h), dev_guard__.err)
 
 // --------------------------------------------------------------------------------------------------
 // The normalised problem.  Every (side, uplo, trans) combination is reduced to
@@ -224,11 +262,7 @@ static bool tma_ok(const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
 
 template <int AMAJ, int BMAJ>
 static int launch_gemm_f64_tma(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB, const GemmF64Params& gp, cudaStream_t st) {
-  static bool configured[64] = {false};  // per device (one handle drives one device)
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_f64_tma_kernel<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM_BYTES));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, gemm_f64_tma_kernel<AMAJ, BMAJ>, GF_SMEM_BYTES); if (arc != NLA_OK) return arc; }
   gemm_f64_tma_kernel<AMAJ, BMAJ><<<gp.tiles_m * gp.tiles_n, GF_THREADS, GF_SMEM_BYTES, st>>>(mA, mB, gp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
@@ -237,11 +271,7 @@ static int launch_gemm_f64_tma(nla_context* ctx, const CUtensorMap& mA, const CU
 
 template <int AMAJ, bool LOWER, bool SOLVE>
 static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV, const SlabParams& sp, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(slab_f64_kernel<AMAJ, LOWER, SOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL_SMEM_BYTES));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, slab_f64_kernel<AMAJ, LOWER, SOLVE>, SL_SMEM_BYTES); if (arc != NLA_OK) return arc; }
   const unsigned grid = (unsigned)((sp.v_count + SL_W - 1) / SL_W);
   slab_f64_kernel<AMAJ, LOWER, SOLVE><<<grid, SL_THREADS, SL_SMEM_BYTES, st>>>(mT, mV, sp);
   ctx->launches++;
@@ -283,11 +313,7 @@ static bool tc_ok(const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
 
 template <typename T, int AMAJ, int BMAJ, int BN>
 static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB, const GemmTcParams& gp, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<T, AMAJ, BMAJ, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<T, BN>::SMEM));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, gemm_tc_kernel<T, AMAJ, BMAJ, BN>, TcShape<T, BN>::SMEM); if (arc != NLA_OK) return arc; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(gp.tiles_m * gp.tiles_n)); cfg.blockDim = dim3(TcCfg<T>::THREADS);
   cfg.dynamicSmemBytes = TcShape<T, BN>::SMEM; cfg.stream = st;
@@ -303,11 +329,7 @@ static int launch_gemm_tc_variant(nla_context* ctx, const CUtensorMap& mA, const
 // CTA-pair variant (gemm_tc2.cuh): cluster of 2, M = 256 per tcgen05.mma
 template <typename T, int AMAJ, int BMAJ>
 static int launch_gemm_tc2_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB128, const GemmTcParams& gp, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(gemm_tc2_kernel<T, AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Shape<T>::SMEM));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, gemm_tc2_kernel<T, AMAJ, BMAJ>, Tc2Shape<T>::SMEM); if (arc != NLA_OK) return arc; }
   const int pairs_m = (gp.tiles_m + 1) / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs_m * gp.tiles_n)); cfg.blockDim = dim3(TcCfg<T>::THREADS);
@@ -324,11 +346,7 @@ static int launch_gemm_tc2_variant(nla_context* ctx, const CUtensorMap& mA, cons
 // Persistent CTA-pair variant (gemm_tc3.cuh, Float16): one cluster per TPC walks a static tile list
 template <int AMAJ, int BMAJ>
 static int launch_gemm_tc3_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB128, const GemmTcParams& gp, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, (cudaFuncSetAttribute(gemm_tc3_kernel<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc3Shape::SMEM)));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, gemm_tc3_kernel<AMAJ, BMAJ>, Tc3Shape::SMEM); if (arc != NLA_OK) return arc; }
   const int64_t ntiles = (int64_t)((gp.tiles_m + 1) / 2) * gp.tiles_n;
   const int64_t ncl = std::min<int64_t>(ntiles, std::max(1, ctx->sm_count / 2));
   cudaLaunchConfig_t cfg{};
@@ -346,11 +364,7 @@ static int launch_gemm_tc3_variant(nla_context* ctx, const CUtensorMap& mA, cons
 // Persistent CTA-pair variant with 256 x 512 tiles (gemm_tc4.cuh, Float16, long updates)
 template <int AMAJ, int BMAJ>
 static int launch_gemm_tc4_variant(nla_context* ctx, const CUtensorMap& mA, const CUtensorMap& mB128, const GemmTcParams& gp, cudaStream_t st) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, (cudaFuncSetAttribute(gemm_tc4_kernel<AMAJ, BMAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc4Shape::SMEM)));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, gemm_tc4_kernel<AMAJ, BMAJ>, Tc4Shape::SMEM); if (arc != NLA_OK) return arc; }
   const int64_t ntiles = (int64_t)((gp.tiles_m + 1) / 2) * gp.tiles_n;
   const int64_t ncl = std::min<int64_t>(ntiles, std::max(1, ctx->sm_count / 2));
   cudaLaunchConfig_t cfg{};
@@ -438,11 +452,7 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
 template <typename T, typename TO = T>
 static int launch_diag_prep(nla_context* ctx, const T* A, int64_t t_rs, int64_t t_cs, int64_t n, bool lower, bool solve, int64_t block0,
                             int64_t nblocks, TO* W, cudaStream_t st, int64_t ib = DP_B, bool unit = false) {
-  static bool configured[64] = {false};
-  if (!configured[ctx->device & 63]) {
-    NLA_CUDA(ctx, (cudaFuncSetAttribute(diag_prep_kernel<T, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES)));
-    configured[ctx->device & 63] = true;
-  }
+  { int arc = ensure_smem_attr(ctx, diag_prep_kernel<T, TO>, DP_SMEM_BYTES); if (arc != NLA_OK) return arc; }
   DiagPrepParams<T, TO> dp;
   dp.A = A; dp.t_rs = t_rs; dp.t_cs = t_cs; dp.n = (int)n; dp.lower = lower; dp.solve = solve; dp.block0 = (int)block0; dp.W = W;
   dp.pitch = (int)ib; dp.ib = (int)ib; dp.unit = unit;
@@ -475,13 +485,64 @@ struct TmaMaps {
 template <typename T> struct InvAcc { using type = float; };
 template <> struct InvAcc<float> { using type = double; };
 
-static int grow_ws(nla_context* ctx, void** ptr, size_t* have, size_t need) {
+// Conditioning guard of the block-inverse leaves (tri_guard.cuh): a block is rejected when  ||T||_F ||inv T||_F / order  exceeds
+// kappa_max = 1 / (32 eps_T): 64 for Float16 (eps 2^-11), 524288 for Float32 (eps 2^-24) -- the point where eps * cond reaches a few per
+// cent, i.e. where the inverse-based leaf starts to lose the digits substitution keeps (measured: DESIGN.md 4.7).
+template <typename T>
+static double guard_thr2(const nla_context* ctx, int64_t ib) {
+  const double kmax = ctx->inv_guard_kappa > 0 ? (double)ctx->inv_guard_kappa : (sizeof(T) == 2 ? 64.0 : 524288.0);
+  const double t = kmax * (double)ib;
+  return t * t;
+}
+
+// ---- device workspaces ----------------------------------------------------------------------------------------------------
+// Library-owned buffers grow with the STREAM-ORDERED allocator (cudaMallocAsync / cudaFreeAsync on the call's stream): growing a
+// workspace neither synchronises the device nor blocks the host, so nla_rectrxm stays asynchronous on its first (or a larger) call.
+// nla_reserve pre-sizes them, nla_set_workspace replaces them by a caller-provided arena (then the library allocates nothing).
+static int grow_ws(nla_context* ctx, void** ptr, size_t* have, size_t need, cudaStream_t st) {
   if (*have >= need) return NLA_OK;
-  if (*ptr) cudaFree(*ptr);
+  if (ctx->user_ws) return NLA_ERR_WORKSPACE;   // carved from the caller's arena by acquire_ws: cannot grow
+  if (*ptr) { NLA_CUDA(ctx, cudaFreeAsync(*ptr, st)); }
   *ptr = nullptr; *have = 0;
-  NLA_CUDA(ctx, cudaMalloc(ptr, need));
+  cudaError_t e = cudaMallocAsync(ptr, need, st);
+  if (e != cudaSuccess) { ctx->last_cuda = (int)e; cudaGetLastError(); *ptr = nullptr; return NLA_ERR_CUDA; }
+  ctx->ws_allocs++;
   *have = need;
   return NLA_OK;
+}
+
+struct WsNeed { size_t diag, acc, u, bcopy, cond; };
+static inline size_t ws_align(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline size_t ws_total(const WsNeed& w) { return ws_align(w.diag) + ws_align(w.acc) + ws_align(w.u) + ws_align(w.bcopy) + ws_align(w.cond); }
+
+// Make the five workspaces at least `need` large: carved from the caller's arena when one is set, grown otherwise.
+static int acquire_ws(nla_context* ctx, const WsNeed& need, cudaStream_t st) {
+  if (ctx->user_ws) {
+    if (ws_total(need) > ctx->user_ws_bytes) return NLA_ERR_WORKSPACE;
+    char* p = (char*)ctx->user_ws;
+    ctx->diag_ws = p; ctx->diag_ws_bytes = need.diag; p += ws_align(need.diag);
+    ctx->inv_acc = p; ctx->inv_acc_bytes = need.acc; p += ws_align(need.acc);
+    ctx->inv_u = p; ctx->inv_u_bytes = need.u; p += ws_align(need.u);
+    ctx->bcopy_ws = p; ctx->bcopy_ws_bytes = need.bcopy; p += ws_align(need.bcopy);
+    ctx->cond_ws = p; ctx->cond_ws_bytes = need.cond;
+    return NLA_OK;
+  }
+  int rc;
+  if ((rc = grow_ws(ctx, &ctx->diag_ws, &ctx->diag_ws_bytes, need.diag, st)) != NLA_OK) return rc;
+  if ((rc = grow_ws(ctx, &ctx->inv_acc, &ctx->inv_acc_bytes, need.acc, st)) != NLA_OK) return rc;
+  if ((rc = grow_ws(ctx, &ctx->inv_u, &ctx->inv_u_bytes, need.u, st)) != NLA_OK) return rc;
+  if ((rc = grow_ws(ctx, &ctx->bcopy_ws, &ctx->bcopy_ws_bytes, need.bcopy, st)) != NLA_OK) return rc;
+  return grow_ws(ctx, &ctx->cond_ws, &ctx->cond_ws_bytes, need.cond, st);
+}
+
+// library-owned workspaces are returned to the stream-ordered pool; an arena of the caller is simply forgotten
+static void release_ws(nla_context* ctx) {
+  void** ptrs[5] = {&ctx->diag_ws, &ctx->inv_acc, &ctx->inv_u, &ctx->bcopy_ws, &ctx->cond_ws};
+  size_t* sizes[5] = {&ctx->diag_ws_bytes, &ctx->inv_acc_bytes, &ctx->inv_u_bytes, &ctx->bcopy_ws_bytes, &ctx->cond_ws_bytes};
+  for (int i = 0; i < 5; i++) {
+    if (*ptrs[i] && !ctx->user_ws) cudaFreeAsync(*ptrs[i], 0);
+    *ptrs[i] = nullptr; *sizes[i] = 0;
+  }
 }
 
 // One update  V[c-range] <- post*(beta*V[c-range] + sgn*Teff[c-range,k-range]*V[k-range])  for vectors [v0, v0+nv)
@@ -600,16 +661,34 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
       NLA_CUDA(ctx, cudaMemcpy2DAsync(ws + v0, (size_t)maps.ws_ld * sizeof(T), B + v0 + o.off * P.ldb, (size_t)P.ldb * sizeof(T),
                                       (size_t)nv * sizeof(T), (size_t)o.sz, cudaMemcpyDeviceToDevice, st));
     }
+    double* rec = ctx->inv_guard ? (double*)ctx->cond_ws + 4 * (o.off / maps.ib) : nullptr;
+    gp.skip_rec = rec; gp.skip_thr2 = guard_thr2<T>(ctx, maps.ib);
+    int rc;
     if (!P.right) {
       gp.M = (int)o.sz; gp.N = (int)nv; gp.win_on_n = 0;
       gp.a_mn0 = (int)o.off; gp.a_k0 = 0; gp.b_mn0 = (int)v0; gp.b_k0 = 0;
       gp.C = B + o.off + v0 * P.ldb;
-      return launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, last ? maps.mapSLast : maps.mapS, last ? maps.mapSLast128 : maps.mapS128, gp, st);
+      rc = launch_gemm_tc<T>(ctx, MAJ_K, MAJ_K, maps.mapW, last ? maps.mapSLast : maps.mapS, last ? maps.mapSLast128 : maps.mapS128, gp, st);
+    } else {
+      gp.M = (int)nv; gp.N = (int)o.sz; gp.win_on_n = 1;
+      gp.a_mn0 = (int)v0; gp.a_k0 = 0; gp.b_mn0 = (int)o.off; gp.b_k0 = 0;
+      gp.C = B + v0 + o.off * P.ldb;
+      rc = launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, last ? maps.mapSLast : maps.mapS, maps.mapW, maps.mapW128, gp, st, 128);
     }
-    gp.M = (int)nv; gp.N = (int)o.sz; gp.win_on_n = 1;
-    gp.a_mn0 = (int)v0; gp.a_k0 = 0; gp.b_mn0 = (int)o.off; gp.b_k0 = 0;
-    gp.C = B + v0 + o.off * P.ldb;
-    return launch_gemm_tc<T>(ctx, MAJ_MN, MAJ_K, last ? maps.mapSLast : maps.mapS, maps.mapW, maps.mapW128, gp, st, 128);
+    if (rc != NLA_OK || !rec) return rc;
+    // the substitution fallback: returns at once unless the guard rejected this block (then the GEMM above did nothing and the
+    // block of V is still untouched in B)
+    TriSubstParams<T> sp;
+    sp.A = (const T*)P.A; sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
+    sp.off = (int)o.off; sp.sz = (int)o.sz; sp.unit = P.unit;
+    sp.V = B; sp.es = P.es; sp.vs = P.vs; sp.v0 = (int)v0; sp.nv = (int)nv;
+    sp.scale = (float)(o.pre * o.post); sp.rec = rec; sp.thr2 = gp.skip_thr2; sp.counter = rec + 3;
+    const unsigned grid = (unsigned)((nv + TS_THREADS - 1) / TS_THREADS);
+    if (P.lower) tri_subst_kernel<T, true><<<grid, TS_THREADS, 0, st>>>(sp);
+    else tri_subst_kernel<T, false><<<grid, TS_THREADS, 0, st>>>(sp);
+    ctx->launches++;
+    NLA_CUDA(ctx, cudaGetLastError());
+    return NLA_OK;
   }
   if (!P.right) {
     gp.M = (int)o.sz; gp.N = (int)nv;
@@ -709,7 +788,30 @@ static int64_t default_leaf(int dtype) { (void)dtype; return LEAF_MAX; }
 struct Plan {
   std::vector<Op> ops;
   TmaMaps maps;
+  bool batched = false;   // Float32/Float16 multiply: the out-of-place batched schedule (trmm_batched_tc) has its copy of B
 };
+
+// Workspace bytes of a Float32/Float16 call on the tensor-core path: prepared diagonal blocks (n x ib), for a block-inverse solve the two
+// accumulation-type copies of the doubling, the out-of-place copy of one leaf's block of V and the conditioning record per block;
+// for the batched multiply one pristine copy of B.
+template <typename T>
+static WsNeed tc_ws_need(const Problem& P, int64_t ib, bool batched) {
+  using Acc = typename InvAcc<T>::type;
+  WsNeed w{};
+  const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
+  w.diag = (size_t)nblocks * DP_B * ib * sizeof(T);
+  if (ib > DP_B) {
+    w.acc = w.u = (size_t)nblocks * DP_B * ib * sizeof(Acc);
+    const int64_t ws_ld = P.right ? ((P.m + 15) & ~15ll) : ib;
+    w.bcopy = (size_t)(P.right ? ws_ld * ib : ib * P.m) * sizeof(T);
+    w.cond = (size_t)((P.n + ib - 1) / ib) * 4 * sizeof(double);
+  }
+  if (batched) {
+    const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
+    w.bcopy = std::max(w.bcopy, (size_t)((brows + 15) & ~15ll) * bcols * sizeof(T));
+  }
+  return w;
+}
 
 // Order of the inverted diagonal blocks of a Float32/Float16 solve: option "inv_block", default 1024 (measured),
 // never more than the smallest power of two covering n.
@@ -721,7 +823,7 @@ static int64_t pick_inv_block(nla_context* ctx, const Problem& P, bool allow) {
 }
 
 template <typename T>
-static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, bool allow_inv = true) {
+static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_t st, bool allow_inv = true, bool allow_batched = true) {
   const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
   std::vector<Op>& ops = plan.ops;
   TmaMaps& maps = plan.maps;
@@ -736,18 +838,19 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, bool allow_
     // base and column pitch); cutoff = 128 = the M tile of one tcgen05.mma.  Otherwise the generic strided kernels.
     if (!ctx->force_simt && ctx->encode && tc_ok<T>(P.A, P.n, P.n, P.lda) && tc_ok<T>(P.B, brows, bcols, P.ldb)) {
       const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
-      const int64_t ib = pick_inv_block(ctx, P, allow_inv);   // 128: the prepared 128-blocks are the leaves' operands
-      using Acc = typename InvAcc<T>::type;
-      int wrc = grow_ws(ctx, &ctx->diag_ws, &ctx->diag_ws_bytes, (size_t)nblocks * DP_B * ib * sizeof(T));
+      int64_t ib = pick_inv_block(ctx, P, allow_inv);   // 128: the prepared 128-blocks are the leaves' operands
+      bool batched = !P.solve && ctx->trmm_batched && allow_batched;
+      // Workspaces.  When the full set cannot be had (allocation failure, or a caller-provided arena that is too small) the call degrades
+      // instead of failing: first to 128-wide leaves (no block inverses), then to the in-place multiply (no copy of B).
+      int wrc = acquire_ws(ctx, tc_ws_need<T>(P, ib, batched), st);
+      if (wrc != NLA_OK && ib > DP_B) { ib = DP_B; wrc = acquire_ws(ctx, tc_ws_need<T>(P, ib, batched), st); }
+      if (wrc != NLA_OK && batched) { batched = false; wrc = acquire_ws(ctx, tc_ws_need<T>(P, ib, batched), st); }
       if (wrc != NLA_OK) return wrc;
+      plan.batched = batched;
       bool ok = true;
       if (ib > DP_B) {
-        if ((wrc = grow_ws(ctx, &ctx->inv_acc, &ctx->inv_acc_bytes, (size_t)nblocks * DP_B * ib * sizeof(Acc))) != NLA_OK) return wrc;
-        if ((wrc = grow_ws(ctx, &ctx->inv_u, &ctx->inv_u_bytes, (size_t)nblocks * DP_B * ib * sizeof(Acc))) != NLA_OK) return wrc;
         // copy of one block of V: ib x m (left side, pitch ib) or m x ib (right side, pitch m rounded up to 16 elements)
         maps.ws_ld = P.right ? ((P.m + 15) & ~15ll) : ib;
-        const size_t need = (size_t)(P.right ? maps.ws_ld * ib : ib * P.m) * sizeof(T);
-        if ((wrc = grow_ws(ctx, &ctx->bcopy_ws, &ctx->bcopy_ws_bytes, need)) != NLA_OK) return wrc;
         const int64_t lastsz = P.n % ib ? P.n % ib : ib;
         if (!P.right) {
           ok = encode_map_tc<T>(ctx, &maps.mapS, ctx->bcopy_ws, ib, P.m, ib, MAJ_K, false) &&
@@ -771,6 +874,7 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, bool allow_
       if (ok) {
         maps.tc = true;
         maps.ib = ib;
+        ctx->cond_blocks = (ib > DP_B && P.solve && ctx->inv_guard) ? (P.n + ib - 1) / ib : 0;
         build_schedule(P, ib, 0, P.n, false, true, ops);
         return NLA_OK;
       }
@@ -818,13 +922,7 @@ template <typename T>
 static int trmm_batched_tc(nla_context* ctx, const Problem& P, const TmaMaps& maps, cudaStream_t st) {
   const int64_t brows = P.right ? P.m : P.n, bcols = P.right ? P.n : P.m;
   const int64_t ldc = (brows + 15) & ~15ll;   // compact pitch, 16-byte aligned for any element size
-  const size_t need = (size_t)ldc * bcols * sizeof(T);
-  if (ctx->bcopy_ws_bytes < need) {
-    if (ctx->bcopy_ws) cudaFree(ctx->bcopy_ws);
-    ctx->bcopy_ws = nullptr; ctx->bcopy_ws_bytes = 0;
-    NLA_CUDA(ctx, cudaMalloc(&ctx->bcopy_ws, need));
-    ctx->bcopy_ws_bytes = need;
-  }
+  if (ctx->bcopy_ws_bytes < (size_t)ldc * bcols * sizeof(T)) return NLA_ERR_WORKSPACE;   // sized by make_plan (tc_ws_need)
   CUtensorMap mapC, mapC128;
   if (!encode_map_tc<T>(ctx, &mapC, ctx->bcopy_ws, brows, bcols, ldc, maps.majV, P.right) ||
       !encode_map_tc<T>(ctx, &mapC128, ctx->bcopy_ws, brows, bcols, ldc, maps.majV, P.right, 128))
@@ -918,6 +1016,18 @@ static int prepare_block_inverses(nla_context* ctx, const Problem& P, int64_t ib
   const unsigned cgrid = (unsigned)std::min<int64_t>(((r1 - r0) * ib + 255) / 256, (int64_t)ctx->sm_count * 16);
   tri_inv_convert_kernel<T, Acc><<<cgrid, 256, 0, st>>>((const Acc*)ctx->inv_acc, (T*)ctx->diag_ws, (int)P.n, (int)r0, (int)r1, (int)ib, P.lower ? 1 : 0);
   ctx->launches++;
+  if (ctx->inv_guard) {
+    // conditioning record of every block of this range: ||Teff_blk||_F^2, ||inverse||_F^2, non-finite entries (tri_guard.cuh)
+    const int64_t b0 = r0 / ib, b1 = (std::min(P.n, r1) + ib - 1) / ib;
+    if (b1 > b0) {
+      NLA_CUDA(ctx, cudaMemsetAsync((double*)ctx->cond_ws + 4 * b0, 0, (size_t)(b1 - b0) * 4 * sizeof(double), st));
+      TriCondParams<T> cp;
+      cp.A = (const T*)P.A; cp.t_rs = t_rs; cp.t_cs = t_cs; cp.n = (int)P.n; cp.ib = (int)ib; cp.lower = P.lower; cp.unit = P.unit;
+      cp.blk0 = (int)b0; cp.W = (const T*)ctx->diag_ws; cp.rec = (double*)ctx->cond_ws;
+      tri_cond_kernel<T><<<dim3(32, (unsigned)(b1 - b0)), 256, 0, st>>>(cp);
+      ctx->launches++;
+    }
+  }
   NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
 }
@@ -944,25 +1054,27 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
     const size_t need = (size_t)P.n * (size_t)P.m * sizeof(double);
     if (P.right && ctx->right_via_left && !ctx->force_simt && ctx->encode && ctx->macro >= 8 && P.n % 8 == 0 && P.n >= 256 && P.m >= 128 &&
         need <= ((size_t)8 << 30) && tma_ok(P.A, P.n, P.n, P.lda)) {
-      int wrc = grow_ws(ctx, &ctx->bcopy_ws, &ctx->bcopy_ws_bytes, need);
-      if (wrc != NLA_OK) return wrc;
-      double* ws = (double*)ctx->bcopy_ws;
-      dim3 g1((unsigned)((P.m + 31) / 32), (unsigned)((P.n + 31) / 32));   // B is m x n
-      transpose_f64_kernel<<<g1, 256, 0, stream>>>((const double*)P.B, P.ldb, ws, P.n, P.m, P.n);
-      ctx->launches++;
-      Problem L = P;
-      L.right = false; L.B = ws; L.ldb = P.n; L.es = 1; L.vs = P.n;   // teff_trans / lower already describe Teff, which is unchanged
-      int rc = rectrxm_typed<double>(ctx, L, stream, gate);
-      if (rc != NLA_OK) return rc;
-      dim3 g2((unsigned)((P.n + 31) / 32), (unsigned)((P.m + 31) / 32));
-      transpose_f64_kernel<<<g2, 256, 0, stream>>>(ws, P.n, (double*)P.B, P.ldb, P.n, P.m);
-      ctx->launches++;
-      NLA_CUDA(ctx, cudaGetLastError());
-      return NLA_OK;
+      WsNeed w{};
+      w.bcopy = need;
+      if (acquire_ws(ctx, w, stream) == NLA_OK) {   // (no room for the copy: the native right-side schedule below needs none)
+        double* ws = (double*)ctx->bcopy_ws;
+        dim3 g1((unsigned)((P.m + 31) / 32), (unsigned)((P.n + 31) / 32));   // B is m x n
+        transpose_f64_kernel<<<g1, 256, 0, stream>>>((const double*)P.B, P.ldb, ws, P.n, P.m, P.n);
+        ctx->launches++;
+        Problem L = P;
+        L.right = false; L.B = ws; L.ldb = P.n; L.es = 1; L.vs = P.n;   // teff_trans / lower already describe Teff, which is unchanged
+        int rc = rectrxm_typed<double>(ctx, L, stream, gate);
+        if (rc != NLA_OK) return rc;
+        dim3 g2((unsigned)((P.n + 31) / 32), (unsigned)((P.m + 31) / 32));
+        transpose_f64_kernel<<<g2, 256, 0, stream>>>(ws, P.n, (double*)P.B, P.ldb, P.n, P.m);
+        ctx->launches++;
+        NLA_CUDA(ctx, cudaGetLastError());
+        return NLA_OK;
+      }
     }
   }
   Plan plan;
-  int prc = make_plan<T>(ctx, P, plan);
+  int prc = make_plan<T>(ctx, P, plan, stream);
   if (prc != NLA_OK) return prc;
   const std::vector<Op>& ops = plan.ops;
   const TmaMaps& maps = plan.maps;
@@ -1024,7 +1136,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
         }
       } else rc = launch_diag_prep<T>(ctx, (const T*)P.A, t_rs, t_cs, P.n, P.lower, P.solve, 0, (P.n + DP_B - 1) / DP_B, (T*)ctx->diag_ws, stream, DP_B, P.unit);
       if (rc != NLA_OK) return rc;
-      if (!P.solve && ctx->trmm_batched) return trmm_batched_tc<T>(ctx, P, maps, stream);
+      if (plan.batched) return trmm_batched_tc<T>(ctx, P, maps, stream);
     }
   }
 
@@ -1101,6 +1213,8 @@ const char* nla_status_string(int status) {
     case NLA_ERR_NO_DEVICE: return "no CUDA device";
     case NLA_ERR_UNSUPPORTED: return "unsupported";
     case NLA_ERR_INVALID_HANDLE: return "invalid handle";
+    case NLA_ERR_WORKSPACE: return "caller-provided workspace too small (see nla_workspace_bytes)";
+    case NLA_ERR_NCCL: return "NCCL error or libnccl not loadable";
   }
   return "unknown status";
 }
@@ -1124,7 +1238,10 @@ int nla_create(nla_handle_t* handle, int device) {
   ctx->inv_dup = 1; ctx->inv_block = 0; ctx->inv_acc = ctx->inv_u = nullptr; ctx->inv_acc_bytes = ctx->inv_u_bytes = 0;
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
-  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
+  ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
+  ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0;
+  DeviceGuard dg(device);
+  if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
@@ -1136,7 +1253,8 @@ int nla_create(nla_handle_t* handle, int device) {
 
 int nla_destroy(nla_handle_t h) {
   if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
-  cudaSetDevice(h->device);
+  DeviceGuard dg(h->device);
+  cudaDeviceSynchronize();   // work of this handle may still be in flight on the caller's streams
   for (auto s : h->streams) cudaStreamDestroy(s);
   for (auto e : h->events) cudaEventDestroy(e);
   for (auto& pr : h->prof) { cudaEventDestroy(pr.e0); cudaEventDestroy(pr.e1); }
@@ -1146,13 +1264,10 @@ int nla_destroy(nla_handle_t h) {
   for (auto e : h->host_events) if (e) cudaEventDestroy(e);
   if (h->stage_a) cudaFree(h->stage_a);
   if (h->stage_b) cudaFree(h->stage_b);
-  if (h->diag_ws) cudaFree(h->diag_ws);
-  if (h->bcopy_ws) cudaFree(h->bcopy_ws);
+  release_ws(h);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
   for (auto e : h->panel_prep_events) cudaEventDestroy(e);
-  if (h->inv_acc) cudaFree(h->inv_acc);
-  if (h->inv_u) cudaFree(h->inv_u);
   h->magic = 0;
   delete h;
   return NLA_OK;
@@ -1182,6 +1297,9 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
     if (value != 0 && (value < 128 || value > 4096 || (value & (value - 1)))) return NLA_ERR_INVALID_DIM;
     h->inv_block = value; return NLA_OK;
   }
+  if (!strcmp(key, "inv_guard")) { h->inv_guard = value != 0; return NLA_OK; }
+  if (!strcmp(key, "inv_guard_kappa")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->inv_guard_kappa = value; return NLA_OK; }
+  if (!strcmp(key, "nvtx")) { h->nvtx = value != 0; return NLA_OK; }
   if (!strcmp(key, "tc_dbg")) { h->tc_dbg = value; return NLA_OK; }
   if (!strcmp(key, "tc_chunk_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_chunk_k = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
@@ -1208,6 +1326,19 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "right_via_left")) return h->right_via_left;
   if (!strcmp(key, "tc_wide_k")) return h->tc_wide_k;
   if (!strcmp(key, "host_slabs")) return h->host_slabs;
+  if (!strcmp(key, "inv_guard")) return h->inv_guard;
+  if (!strcmp(key, "inv_guard_kappa")) return h->inv_guard_kappa;
+  if (!strcmp(key, "inv_fallbacks")) {   // read-only, synchronises: blocks of the LAST guarded solve that took the substitution fallback
+    if (!h->cond_ws || h->cond_blocks <= 0) return 0;
+    DeviceGuard dg(h->device);
+    std::vector<double> rec((size_t)h->cond_blocks * 4);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(rec.data(), h->cond_ws, rec.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t cnt = 0;
+    for (int64_t b = 0; b < h->cond_blocks; b++) cnt += rec[(size_t)b * 4 + 3] > 0.0;
+    return cnt;
+  }
+  if (!strcmp(key, "nvtx")) return h->nvtx;
+  if (!strcmp(key, "ws_allocs")) return h->ws_allocs;   // read-only counter
   return -1;
 }
 
@@ -1244,6 +1375,95 @@ int64_t nla_launch_count(nla_handle_t h, int reset) {
   return c;
 }
 
+int nla_probe_fp64_peak(nla_handle_t h, double* tflops) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (!tflops) return NLA_ERR_NULL_POINTER;
+  NLA_ON_DEVICE(h);
+  double* out = nullptr;
+  NLA_CUDA(h, cudaMalloc(&out, 256));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 20000, warps = 32;
+  float best = 1e30f;
+  cudaError_t err = cudaSuccess;
+  for (int r = 0; r < 4 && err == cudaSuccess; r++) {   // first repetition = warm-up
+    cudaEventRecord(e0, 0);
+    dmma_peak_kernel<<<h->sm_count, warps * 32>>>(out, iters);
+    cudaEventRecord(e1, 0);
+    err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  h->launches += 4;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess) { h->last_cuda = (int)err; return NLA_ERR_CUDA; }
+  // 4 DMMAs per warp per iteration, 8 x 8 x 4 x 2 flops each
+  *tflops = (double)h->sm_count * warps * (double)iters * 4.0 * 512.0 / ((double)best * 1e-3) * 1e-12;
+  return NLA_OK;
+}
+
+// ---- workspace control ------------------------------------------------------------------------------------
+static int ws_need_for(nla_context* h, char side, char func, int dtype, int64_t n, int64_t m, WsNeed& w) {
+  Problem P;
+  int rc = make_problem(P, side, 'L', 'N', func, dtype, n, m, 1.0, (const void*)16, std::max<int64_t>(1, n), (void*)16,
+                        std::max<int64_t>(1, side == 'R' ? m : n));
+  if (rc != NLA_OK) return rc;
+  w = WsNeed{};
+  if (n == 0 || m == 0) return NLA_OK;
+  if (dtype == NLA_F64) {
+    const size_t need = (size_t)n * (size_t)m * sizeof(double);
+    if (P.right && h->right_via_left && need <= ((size_t)8 << 30)) w.bcopy = need;
+    return NLA_OK;
+  }
+  const int64_t ib = pick_inv_block(h, P, true);
+  const bool batched = !P.solve && h->trmm_batched;
+  w = dtype == NLA_F32 ? tc_ws_need<float>(P, ib, batched) : tc_ws_need<__half>(P, ib, batched);
+  return NLA_OK;
+}
+
+int64_t nla_workspace_bytes(nla_handle_t h, char side, char func, int dtype, int64_t n, int64_t m) {
+  if (!valid(h)) return -NLA_ERR_INVALID_HANDLE;
+  WsNeed w;
+  int rc = ws_need_for(h, side, func, dtype, n, m, w);
+  if (rc != NLA_OK) return -rc;
+  return (int64_t)ws_total(w);
+}
+
+int nla_set_workspace(nla_handle_t h, void* workspace, int64_t bytes) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (bytes < 0 || (workspace && ((uintptr_t)workspace % 256))) return NLA_ERR_INVALID_DIM;
+  NLA_ON_DEVICE(h);
+  if (!h->user_ws) release_ws(h);                                // library-owned buffers go back to the pool
+  else { h->diag_ws = h->inv_acc = h->inv_u = h->bcopy_ws = h->cond_ws = nullptr; h->diag_ws_bytes = h->inv_acc_bytes = h->inv_u_bytes = h->bcopy_ws_bytes = h->cond_ws_bytes = 0; }
+  h->user_ws = bytes > 0 ? workspace : nullptr;
+  h->user_ws_bytes = h->user_ws ? (size_t)bytes : 0;
+  return NLA_OK;
+}
+
+int nla_reserve(nla_handle_t h, char side, char func, int dtype, int64_t n, int64_t m) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  WsNeed w;
+  int rc = ws_need_for(h, side, func, dtype, n, m, w);
+  if (rc != NLA_OK) return rc;
+  NLA_ON_DEVICE(h);
+  if (h->user_ws) return ws_total(w) <= h->user_ws_bytes ? NLA_OK : NLA_ERR_WORKSPACE;
+  // never shrink: keep what earlier calls / reservations obtained
+  w.diag = std::max(w.diag, h->diag_ws_bytes); w.acc = std::max(w.acc, h->inv_acc_bytes); w.u = std::max(w.u, h->inv_u_bytes);
+  w.bcopy = std::max(w.bcopy, h->bcopy_ws_bytes); w.cond = std::max(w.cond, h->cond_ws_bytes);
+  rc = acquire_ws(h, w, 0);
+  if (rc != NLA_OK) return rc;
+  NLA_CUDA(h, cudaStreamSynchronize(0));
+  // helper streams / events the calls would otherwise create lazily
+  if ((rc = ensure_streams(h, 4)) != NLA_OK) return rc;
+  if (!h->prep_stream) {
+    NLA_CUDA(h, cudaStreamCreateWithFlags(&h->prep_stream, cudaStreamNonBlocking));
+    NLA_CUDA(h, cudaEventCreateWithFlags(&h->prep_event, cudaEventDisableTiming));
+  }
+  return NLA_OK;
+}
+
 int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t* out, int64_t max_ops) {
   Problem P;
   int rc = make_problem(P, side, uplo, trans, func, NLA_F64, n, 1, 2.0, (const void*)8, std::max<int64_t>(1, n), (void*)8, std::max<int64_t>(1, n));
@@ -1272,7 +1492,7 @@ int nla_rectrxm(nla_handle_t h, char side, char uplo, char trans, char func, int
   int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A, lda, B, ldb);
   if (rc != NLA_OK) return rc;
   if (n == 0 || m == 0) return NLA_OK;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   return dispatch(h, P, (cudaStream_t)stream);
 }
 
@@ -1287,7 +1507,7 @@ int nla_rectrxm_gated(nla_handle_t h, char side, char uplo, char trans, char fun
   if (n_panels > 0 && !panel_events) return NLA_ERR_NULL_POINTER;
   for (int64_t p = 0; p < n_panels; p++) if (!panel_events[p]) return NLA_ERR_NULL_POINTER;
   if (n == 0 || m == 0) return NLA_OK;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   Gate gate{panel_cols, n_panels, (cudaEvent_t const*)panel_events};
   return dispatch(h, P, (cudaStream_t)stream, &gate);
 }
@@ -1327,7 +1547,7 @@ int nla_trxm(nla_handle_t h, char side, char uplo, char trans, char diag, char f
   int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A, lda, B, ldb, diag);
   if (rc != NLA_OK) return rc;
   if (n == 0 || m == 0) return NLA_OK;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   return dispatch(h, P, (cudaStream_t)stream);
 }
 
@@ -1339,7 +1559,7 @@ static int leaf_entry(nla_handle_t h, bool solve, char side, char uplo, int dtyp
   if (rc != NLA_OK) return rc;
   if (n > LEAF_MAX) return NLA_ERR_INVALID_DIM;
   if (n == 0 || m == 0) return NLA_OK;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   Op o{};
   o.kind = Op::LEAF; o.off = 0; o.sz = n; o.pre = 1.0; o.post = 1.0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1413,7 +1633,7 @@ int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t
   if (lda < std::max<int64_t>(1, ar) || ldb < std::max<int64_t>(1, br) || ldc < std::max<int64_t>(1, M)) return NLA_ERR_INVALID_DIM;
   if (M == 0 || N == 0 || K == 0) return NLA_OK;
   if (!A || !B || !C) return NLA_ERR_NULL_POINTER;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case NLA_F64: return gemm_update_typed<double>(h, transa, transb, M, N, K, sign, A, lda, B, ldb, C, ldc, st);
@@ -1500,10 +1720,13 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   int rc = make_problem(P, side, uplo, trans, func, dtype, n, m, alpha, A_dev ? A_dev : A_host, A_dev ? lda_dev : lda, B_host, ldb);
   if (rc != NLA_OK) return rc;
   if (n == 0 || m == 0) return NLA_OK;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   const size_t es = dtype_size(dtype);
   const int64_t brows = P.right ? m : n, bcols = P.right ? n : m;
-  const int64_t dlda = A_dev ? lda_dev : ((n + 1) & ~1ll), dldb = (brows + 1) & ~1ll;   // compact, TMA-friendly leading dimensions on the device
+  // compact leading dimensions on the device, rounded up to 16 bytes: the pitch rule of TMA for every element size (2 Float64, 4 Float32,
+  // 8 Float16 elements), so that a ragged n or m never drops the staged copies from the tensor-core path to the generic kernels
+  const int64_t r16 = 16 / (int64_t)es;
+  const int64_t dlda = A_dev ? lda_dev : ((n + r16 - 1) / r16 * r16), dldb = (brows + r16 - 1) / r16 * r16;
   const size_t a_bytes = A_dev ? 0 : (size_t)dlda * n * es, b_bytes = (size_t)dldb * bcols * es;
   if (h->stage_a_bytes < a_bytes) {
     if (h->stage_a) cudaFree(h->stage_a);
@@ -1527,15 +1750,16 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   Plan plan;
   // Float64: fused-slab blocks of at most 1024 here (2048 on device-resident data): the first leaf can start after one chunk of B and the
   // last download is one chunk (measured on C2 with 4 slabs: 142.3 -> 140.9 ms)
-  const int64_t macro_saved = h->macro;
-  if (h->macro > 1024) h->macro = 1024;
-  switch (dtype) {
-    // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived)
-    case NLA_F64: rc = make_plan<double>(h, D, plan, false); break;
-    case NLA_F32: rc = make_plan<float>(h, D, plan, false); break;
-    default: rc = make_plan<__half>(h, D, plan, false); break;
+  {
+    struct MacroRestore { nla_context* c; int64_t v; ~MacroRestore() { c->macro = v; } } restore{h, h->macro};
+    if (h->macro > 1024) h->macro = 1024;
+    switch (dtype) {
+      // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived; in-place multiply)
+      case NLA_F64: rc = make_plan<double>(h, D, plan, s_cmp, false, false); break;
+      case NLA_F32: rc = make_plan<float>(h, D, plan, s_cmp, false, false); break;
+      default: rc = make_plan<__half>(h, D, plan, s_cmp, false, false); break;
+    }
   }
-  h->macro = macro_saved;
   if (rc != NLA_OK) return rc;
   plan.maps.prep_per_leaf = plan.maps.tc;
   // ---- RHS slabs ----
@@ -1569,7 +1793,19 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   const std::vector<int>& need = hp.need;
   const std::vector<int>& b_last = hp.b_last;
 
-  std::vector<cudaEvent_t> in_ev(xfers.size()), out_ev((size_t)(nt * S));
+  // the per-call events are released on EVERY exit path (an error return from the middle of the pipeline included); before that the
+  // streams are drained so that no queued copy outlives the call
+  struct EventSet {
+    nla_context* c; cudaStream_t extra[3]; std::vector<cudaEvent_t> in, out;
+    ~EventSet() {
+      for (auto st : extra) if (st) cudaStreamSynchronize(st);
+      for (auto st : c->streams) cudaStreamSynchronize(st);
+      for (auto e : in) if (e) cudaEventDestroy(e);
+      for (auto e : out) if (e) cudaEventDestroy(e);
+    }
+  } evs{h, {s_in, s_out, s_cmp}, std::vector<cudaEvent_t>(xfers.size(), nullptr), std::vector<cudaEvent_t>((size_t)(nt * S), nullptr)};
+  std::vector<cudaEvent_t>& in_ev = evs.in;
+  std::vector<cudaEvent_t>& out_ev = evs.out;
   for (auto& e : in_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : out_ev) NLA_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
@@ -1633,8 +1869,6 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   NLA_CUDA(h, cudaStreamSynchronize(s_out));
   NLA_CUDA(h, cudaStreamSynchronize(s_cmp));
   NLA_CUDA(h, cudaStreamSynchronize(s_in));
-  for (auto e : in_ev) cudaEventDestroy(e);
-  for (auto e : out_ev) cudaEventDestroy(e);
   return NLA_OK;
 }
 
@@ -1683,7 +1917,7 @@ int nla_memcpy2d_async(nla_handle_t h, void* dst, int64_t dst_pitch_bytes, const
   if (width_bytes < 0 || height < 0 || dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return NLA_ERR_INVALID_DIM;
   if (width_bytes == 0 || height == 0) return NLA_OK;
   if (!dst || !src) return NLA_ERR_NULL_POINTER;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   const cudaMemcpyKind kind = to_device == 2 ? cudaMemcpyDeviceToDevice : to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   NLA_CUDA(h, cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height, kind,
                                 (cudaStream_t)stream));
@@ -1698,7 +1932,7 @@ int nla_laswp(nla_handle_t h, int dtype, int64_t rows, int64_t ncols, void* A, i
   if (ncols == 0 || k2 < k1) return NLA_OK;
   if (k1 < 1 || k2 > rows) return NLA_ERR_INVALID_DIM;
   if (!A || !ipiv) return NLA_ERR_NULL_POINTER;
-  NLA_CUDA(h, cudaSetDevice(h->device));
+  NLA_ON_DEVICE(h);
   const unsigned grid = (unsigned)((ncols + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   const long long* piv = (const long long*)ipiv;

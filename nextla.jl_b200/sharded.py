@@ -150,15 +150,121 @@ def unified_rectrxm_pipelined(side: str, uplo: str, transpose: str, alpha: float
 
 
 _host_pipe = {}
+_upload_streams = {}
 
 
-def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: float, func: str, A_dev, A_host, B_host, src: int = 0,
+def gpu_numa_node(local_rank: int):
+    """NUMA node of a GPU from sysfs (None when it cannot be determined, e.g. single-socket boxes report -1)."""
+    import torch
+
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        return node if node >= 0 else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def _node_cpus(node: int):
+    cpus = set()
+    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+_numa_state = {}
+
+
+def bind_numa_local(local_rank: int) -> bool:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates afterwards
+    (first touch by this process) live in the memory next to that GPU's PCIe root and host<->device copies do not cross the
+    socket interconnect.  One process per GPU: each rank binds itself.  Returns False when the topology is not exposed."""
+    import os
+
+    node = gpu_numa_node(local_rank)
+    info = {"gpu_numa_node": node, "bound": False}
+    try:
+        if node is not None:
+            allowed = os.sched_getaffinity(0)
+            cpus = _node_cpus(node) & allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info.update(bound=True, cpus=len(cpus))
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)
+    _numa_state[local_rank] = info
+    return info["bound"]
+
+
+def numa_report(local_rank: int):
+    return _numa_state.get(local_rank, {"gpu_numa_node": gpu_numa_node(local_rank), "bound": False})
+
+
+class HostSharedMatrix:
+    """An n x n matrix in host memory that EVERY rank of the node can DMA from: a POSIX shared-memory file mapped by all ranks and
+    page-locked by each (cudaHostRegister).  `tensor` is the contiguous (n x n) storage (= the transpose view of the column-major
+    matrix, like A.t() of a device matrix).  Lets each rank upload its share of the panels of A through its own PCIe link."""
+
+    def __init__(self, n: int, dtype, rank: int, local_rank: int, world: int, name: str = "nla_A"):
+        import os
+
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        self.path = f"/dev/shm/{name}_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}"
+        self.rank, self.world = rank, world
+        npdt = {torch.float64: np.float64, torch.float32: np.float32, torch.float16: np.float16}[dtype]
+        nbytes = n * n * np.dtype(npdt).itemsize
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if world > 1:
+            dist.barrier()
+        self.mm = np.memmap(self.path, dtype=npdt, mode="r+", shape=(n, n))
+        self.tensor = torch.from_numpy(self.mm)
+        self.registered = False
+        rc = torch.cuda.cudart().cudaHostRegister(self.tensor.data_ptr(), nbytes, 0)
+        self.registered = int(rc) == 0
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(self.path)     # the mappings keep the memory alive; nothing is left behind in /dev/shm
+            except OSError:
+                pass
+
+    def close(self):
+        import torch
+
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.tensor.data_ptr())
+            self.registered = False
+
+
+def panel_roots(order, world: int, src):
+    """Which rank uploads / broadcasts each panel: `src` when given (A lives in that rank's memory only), otherwise round-robin in
+    consumption order (A in host memory every rank can read: rank k uploads the k-th, (k+N)-th, ... consumed panel)."""
+    if src is not None:
+        return {p: src for p in order}
+    return {p: i % world for i, p in enumerate(order)}
+
+
+def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: float, func: str, A_dev, A_host, B_host, src=0,
                                    group=None, panels: int = 8, handle=None):
-    """End-to-end multi-GPU call with HOST buffers.  `A_host` (pinned, column-major, significant on `src` only) goes
-    host -> owner GPU -> every GPU panel by panel (H2D copy + NCCL broadcast on a side stream, in consumption order) into
-    `A_dev` (column-major, ld = n); the rank's right-hand sides `B_host` (column-major ndarray-like torch CPU tensor, pinned)
-    are streamed through the device by the library's host pipeline (nla_rectrxm_hostb_gated: chunks of B in first-touch
-    order, every launch gated on the panels of A it reads, results copied back as soon as they are final).  Synchronous."""
+    """End-to-end multi-GPU call with HOST buffers.  `A_host` (pinned, column-major) goes host -> GPU -> every GPU panel by panel
+    (H2D copy of the referenced trapezoid + NCCL broadcast, in consumption order) into `A_dev` (column-major, ld = n); the rank's
+    right-hand sides `B_host` (column-major torch CPU tensor, pinned) are streamed through the device by the library's host pipeline
+    (nla_rectrxm_hostb_gated: chunks of B in first-touch order, every launch gated on the panels of A it reads, results copied back as
+    soon as they are final).  Synchronous.
+    src = r: A_host is significant on rank r only; r uploads and broadcasts every panel.
+    src = None: A_host is readable by every rank (HostSharedMatrix); the uploads are spread round-robin over the ranks -- every PCIe
+    link carries 1/N of A next to its own rank's B -- and each rank is the NCCL root of the panels it uploaded."""
     import ctypes
 
     import torch
@@ -167,34 +273,48 @@ def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: 
     from . import _ch, _check, _desc, default_handle, load_library, panel_order
 
     multi = dist.is_initialized() and dist.get_world_size(group) > 1
-    rank = dist.get_rank(group) if multi else src
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else (src if src is not None else 0)
     n = A_dev.shape[0]
     dev = A_dev.device
     if dev not in _host_pipe:
         _host_pipe[dev] = torch.cuda.Stream(device=dev)
-    bs = _host_pipe[dev]
-    bs.wait_stream(torch.cuda.current_stream(dev))
+        _upload_streams[dev] = torch.cuda.Stream(device=dev)
+    bs, us = _host_pipe[dev], _upload_streams[dev]
+    cur = torch.cuda.current_stream(dev)
+    bs.wait_stream(cur)
+    us.wait_stream(cur)
     pc, npan = panel_geometry(n, panels)
     order = panel_order(side, uplo, transpose, func, n, pc)
+    roots = panel_roots(order, world, src)
     events = [torch.cuda.Event() for _ in range(npan)]
     A_store = A_dev.t()
-    Ah_store = A_host.t() if rank == src else None
     h = handle or default_handle(dev.index)
+    lib = load_library()
+    es = A_dev.element_size()
+    # uploads first, all of this rank's panels in consumption order on their own stream: they start at once on every rank and are
+    # not serialised behind the broadcasts of other ranks' panels
+    up_events = {}
+    for p in order:
+        if roots[p] != rank:
+            continue
+        # only the referenced triangle crosses PCIe: rows [p*pc, n) of a lower panel, [0, (p+1)*pc) of an upper one
+        # (a pitched cudaMemcpy2DAsync: torch's copy_ of a non-contiguous host slice goes through a pageable staging copy and blocks)
+        c0, c1 = p * pc, min(n, (p + 1) * pc)
+        r0, r1 = (c0, n) if uplo == "L" else (0, c1)
+        Ah_store = A_host.t()
+        rc = lib.nla_memcpy2d_async(h._h, A_store.data_ptr() + (c0 * n + r0) * es, n * es,
+                                    Ah_store.data_ptr() + (c0 * Ah_store.stride(0) + r0) * es, Ah_store.stride(0) * es,
+                                    (r1 - r0) * es, c1 - c0, 1, ctypes.c_void_p(us.cuda_stream))
+        _check(rc, h._h)
+        up_events[p] = torch.cuda.Event()
+        up_events[p].record(us)
     with torch.cuda.stream(bs):
         for p in order:
-            rows = slice(p * pc, min(n, (p + 1) * pc))
-            if rank == src:   # only the referenced triangle crosses PCIe: rows [p*pc, n) of a lower panel, [0, (p+1)*pc) of an upper one
-                # (a pitched cudaMemcpy2DAsync: torch's copy_ of a non-contiguous host slice goes through a pageable staging copy
-                #  and blocks -- measured 600 ms per step at 4 GPUs)
-                r0, r1 = (p * pc, n) if uplo == "L" else (0, min(n, (p + 1) * pc))
-                c0, c1 = rows.start, rows.stop
-                es = A_dev.element_size()
-                rc = load_library().nla_memcpy2d_async(h._h, A_store.data_ptr() + (c0 * n + r0) * es, n * es,
-                                                       Ah_store.data_ptr() + (c0 * Ah_store.stride(0) + r0) * es, Ah_store.stride(0) * es,
-                                                       (r1 - r0) * es, c1 - c0, 1, ctypes.c_void_p(bs.cuda_stream))
-                _check(rc, h._h)
+            if p in up_events:
+                bs.wait_event(up_events[p])
             if multi:
-                dist.broadcast(A_store[rows], src=src, group=group)
+                dist.broadcast(A_store[p * pc:min(n, (p + 1) * pc)], src=roots[p], group=group)
             events[p].record(bs)
     pa, ar, ac, lda, dta = _desc(A_dev)
     if B_host.dim() != 2 or (B_host.shape[0] > 1 and B_host.stride(0) != 1):
@@ -202,7 +322,7 @@ def unified_rectrxm_pipelined_host(side: str, uplo: str, transpose: str, alpha: 
     m = B_host.shape[1] if side == "L" else B_host.shape[0]
     ldb = B_host.stride(1) if B_host.shape[1] > 1 else max(1, B_host.shape[0])
     evs = (ctypes.c_void_p * npan)(*[ctypes.c_void_p(e.cuda_event) for e in events])
-    rc = load_library().nla_rectrxm_hostb_gated(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda,
-                                                B_host.data_ptr(), ldb, pc, npan, evs)
+    rc = lib.nla_rectrxm_hostb_gated(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda,
+                                     B_host.data_ptr(), ldb, pc, npan, evs)
     _check(rc, h._h)
     return B_host

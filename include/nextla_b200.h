@@ -91,6 +91,31 @@ int nla_rectrxm_gated(nla_handle_t handle, char side, char uplo, char trans, cha
 int64_t nla_panel_order(char side, char uplo, char trans, char func, int64_t n, int64_t panel_cols, int64_t *order,
                         int64_t max_panels);
 
+/* Single-process multi-GPU: one host thread drives every GPU of the box; the library owns the NCCL communicators
+ * (ncclCommInitAll; libnccl is bound at run time with dlopen, so a process that already carries NCCL shares its copy), per-GPU compute /
+ * broadcast / upload streams, the per-panel events and the replicas of A.  The right-hand sides are sharded by the caller: shard i
+ * (shard_m[i] vectors, leading dimension ldb[i]) lives on GPU i -- columns of B for side 'L', rows for side 'R'.
+ *   nla_mg_create(&mg, ngpu, devices)   devices = NULL: GPUs 0 .. ngpu-1.  ngpu = 1 needs no NCCL.
+ *   nla_mg_rectrxm      A on GPU `root` (device pointer), B shards on their GPUs.  A is broadcast in column panels in the order the schedule
+ *                       consumes them, every GPU's solve gated panel by panel (nla_rectrxm_gated).  ASYNCHRONOUS on the library's streams:
+ *                       A and the shards must be complete when the call is made; nla_mg_sync waits for the results.
+ *   nla_mg_rectrxm_host A and the B shards in HOST memory (pinned for full speed).  The k-th consumed panel of A is uploaded through GPU
+ *                       (k mod ngpu)'s own PCIe link -- only the referenced trapezoid -- and broadcast from there; every GPU streams its shard
+ *                       of B through the host pipeline (nla_rectrxm_hostb_gated), one host thread per GPU inside the call.  Synchronous.
+ *   nla_mg_handle(mg, i) the per-GPU handle (for nla_set_option); nla_mg_stream(mg, i) GPU i's compute stream (cudaStream_t). */
+typedef struct nla_mg_context *nla_mg_t;
+int nla_mg_create(nla_mg_t *mg, int ngpu, const int *devices);
+int nla_mg_destroy(nla_mg_t mg);
+int nla_mg_device_count(nla_mg_t mg);
+nla_handle_t nla_mg_handle(nla_mg_t mg, int i);
+void *nla_mg_stream(nla_mg_t mg, int i);
+int nla_mg_last_nccl_error(nla_mg_t mg);
+int nla_mg_sync(nla_mg_t mg);
+int nla_mg_rectrxm(nla_mg_t mg, char side, char uplo, char trans, char func, int dtype, int64_t n, double alpha, int root,
+                   const void *A_root, int64_t lda, void *const *B_shards, const int64_t *shard_m, const int64_t *ldb);
+int nla_mg_rectrxm_host(nla_mg_t mg, char side, char uplo, char trans, char func, int dtype, int64_t n, double alpha,
+                        const void *A_host, int64_t lda, void *const *B_host_shards, const int64_t *shard_m, const int64_t *ldb);
+
 /* Host B, device A: the multi-GPU end-to-end path.  A is (becoming) resident on this device -- panel_events as in nla_rectrxm_gated,
  * n_panels = 0 if it is already complete -- while this rank's right-hand sides live in host memory: B_host is streamed through
  * the device exactly as in nla_rectrxm_host (chunks in first-touch order, copied back as soon as they are final).  Synchronous. */

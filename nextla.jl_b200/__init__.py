@@ -55,6 +55,15 @@ def load_library():
         "nla_last_cuda_error": (I, [H]),
         "nla_version": (I, []),
         "nla_probe_fp64_peak": (I, [H, c.POINTER(c.c_double)]),
+        "nla_mg_create": (I, [c.POINTER(H), I, c.POINTER(c.c_int)]),
+        "nla_mg_destroy": (I, [H]),
+        "nla_mg_device_count": (I, [H]),
+        "nla_mg_handle": (H, [H, I]),
+        "nla_mg_stream": (P, [H, I]),
+        "nla_mg_last_nccl_error": (I, [H]),
+        "nla_mg_sync": (I, [H]),
+        "nla_mg_rectrxm": (I, [H, CH, CH, CH, CH, I, L, D, I, P, L, c.POINTER(c.c_void_p), c.POINTER(c.c_int64), c.POINTER(c.c_int64)]),
+        "nla_mg_rectrxm_host": (I, [H, CH, CH, CH, CH, I, L, D, P, L, c.POINTER(c.c_void_p), c.POINTER(c.c_int64), c.POINTER(c.c_int64)]),
         "nla_workspace_bytes": (L, [H, CH, CH, I, L, L]),
         "nla_reserve": (I, [H, CH, CH, I, L, L]),
         "nla_set_workspace": (I, [H, P, L]),
@@ -88,6 +97,8 @@ def load_library():
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
             "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak",
+            "nla_mg_create", "nla_mg_destroy", "nla_mg_device_count", "nla_mg_handle", "nla_mg_stream", "nla_mg_last_nccl_error", "nla_mg_sync",
+            "nla_mg_rectrxm", "nla_mg_rectrxm_host",
             "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
             "nla_trsm_leaf", "nla_trmm_leaf", "nla_leaf_max", "nla_gemm_update", "nla_set_option", "nla_get_option", "nla_launch_count", "nla_plan", "nla_profile_read"]
 
@@ -449,6 +460,79 @@ def lauum(uplo: str, A, ib: int = 1024, **kw):
                 GEMM_ADD(A[i0:i1, i1:], A[i0:i1, i1:], tmp, transb="T", **kw)               # rank-k update                (:127-131)
         Aii.copy_(tri(tmp) + anti(Aii, 1 if lower else -1))
     return A
+
+
+class MultiGPU:
+    """Single-process multi-GPU driver (nla_mg_* in the C ABI): one host thread, every GPU of the box; the library owns the NCCL
+    communicators, streams, events and the replicas of A.  The torch.distributed path (sharded.py, one process per GPU) is what
+    bench.py runs under torchrun; this is the same pipeline for a host that has no process group -- e.g. a Julia session."""
+
+    def __init__(self, devices=None, ngpu: Optional[int] = None):
+        import torch
+
+        lib = load_library()
+        if devices is None:
+            devices = list(range(ngpu if ngpu is not None else torch.cuda.device_count()))
+        self.devices = list(devices)
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        self._mg = ctypes.c_void_p()
+        _check(lib.nla_mg_create(ctypes.byref(self._mg), len(self.devices), arr))
+
+    def handle_option(self, i: int, key: str, value: int):
+        h = load_library().nla_mg_handle(self._mg, i)
+        _check(load_library().nla_set_option(h, key.encode(), int(value)))
+
+    def _shards(self, side, shards, host: bool):
+        n_sh = len(self.devices)
+        if len(shards) != n_sh:
+            raise NextLAError(f"expected {n_sh} shards of B, got {len(shards)}")
+        ptrs = (ctypes.c_void_p * n_sh)()
+        ms = (ctypes.c_int64 * n_sh)()
+        lds = (ctypes.c_int64 * n_sh)()
+        for i, b in enumerate(shards):
+            if host:
+                if not b.flags.f_contiguous:
+                    raise NextLAError("host shards must be Fortran-ordered ndarrays")
+                ptrs[i], rows, cols, lds[i] = b.ctypes.data, b.shape[0], b.shape[1], max(1, b.shape[0])
+            else:
+                p, rows, cols, ld, _ = _desc(b)
+                if b.device.index != self.devices[i]:
+                    raise NextLAError(f"shard {i} must live on device {self.devices[i]}")
+                ptrs[i], lds[i] = p, ld
+            ms[i] = cols if side == "L" else rows
+        return ptrs, ms, lds
+
+    def rectrxm(self, side, uplo, transpose, alpha, func, A, root: int, B_shards):
+        """A: column-major matrix on GPU self.devices[root]; B_shards[i]: column-major shard on GPU self.devices[i].  Asynchronous."""
+        pa, ar, ac, lda, dta = _desc(A)
+        if A.device.index != self.devices[root] or ar != ac:
+            raise NextLAError("A must be square and live on the root device")
+        ptrs, ms, lds = self._shards(side, B_shards, False)
+        _check(load_library().nla_mg_rectrxm(self._mg, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, ar, float(alpha), root, pa, lda, ptrs, ms, lds))
+        return B_shards
+
+    def rectrxm_host(self, side, uplo, transpose, alpha, func, A: np.ndarray, B_shards):
+        """A and the shards of B are HOST arrays (Fortran order; page-locked memory for full speed).  Synchronous; shards are overwritten."""
+        if not A.flags.f_contiguous:
+            raise NextLAError("A must be a Fortran-ordered ndarray")
+        ptrs, ms, lds = self._shards(side, B_shards, True)
+        _check(load_library().nla_mg_rectrxm_host(self._mg, _ch(side), _ch(uplo), _ch(transpose), _ch(func), _NP2DT[A.dtype], A.shape[0], float(alpha),
+                                                  A.ctypes.data, max(1, A.shape[0]), ptrs, ms, lds))
+        return B_shards
+
+    def sync(self):
+        _check(load_library().nla_mg_sync(self._mg))
+
+    def close(self):
+        if self._mg:
+            load_library().nla_mg_destroy(self._mg)
+            self._mg = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def host_plan(side: str, uplo: str, transpose: str, func: str, n: int, cutoff: int = 1024, slabs: int = 1, a_resident: bool = False):

@@ -619,6 +619,7 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
   sp.A = (const double*)P.A;
   sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
   sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = o.pre; sp.post = o.post; sp.unit = P.unit;
+  sp.dbg = (unsigned long long*)ctx->tc_dbg;
   const int v = (P.teff_trans ? 4 : 0) | (P.lower ? 2 : 0) | (P.solve ? 1 : 0);
   switch (v) {
     case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
@@ -662,7 +663,7 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
                                       (size_t)nv * sizeof(T), (size_t)o.sz, cudaMemcpyDeviceToDevice, st));
     }
     double* rec = ctx->inv_guard ? (double*)ctx->cond_ws + 4 * (o.off / maps.ib) : nullptr;
-    gp.skip_rec = rec; gp.skip_thr2 = guard_thr2<T>(ctx, maps.ib);
+    gp.skip_rec = rec; gp.skip_thr2 = guard_thr2<T>(ctx, o.sz);   // normalised by the order of THIS block (the last one may be ragged)
     int rc;
     if (!P.right) {
       gp.M = (int)o.sz; gp.N = (int)nv; gp.win_on_n = 0;
@@ -683,11 +684,15 @@ static int launch_leaf_tc(nla_context* ctx, const Problem& P, const TmaMaps& map
     sp.off = (int)o.off; sp.sz = (int)o.sz; sp.unit = P.unit;
     sp.V = B; sp.es = P.es; sp.vs = P.vs; sp.v0 = (int)v0; sp.nv = (int)nv;
     sp.scale = (float)(o.pre * o.post); sp.rec = rec; sp.thr2 = gp.skip_thr2; sp.counter = rec + 3;
-    const unsigned grid = (unsigned)((nv + TS_THREADS - 1) / TS_THREADS);
-    if (P.lower) tri_subst_kernel<T, true><<<grid, TS_THREADS, 0, st>>>(sp);
-    else tri_subst_kernel<T, false><<<grid, TS_THREADS, 0, st>>>(sp);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((nv + TS_THREADS - 1) / TS_THREADS)); cfg.blockDim = dim3(TS_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = ctx->pdl ? 1 : 0;
+    if (P.lower) { NLA_CUDA(ctx, (cudaLaunchKernelEx(&cfg, tri_subst_kernel<T, true>, sp))); }
+    else { NLA_CUDA(ctx, (cudaLaunchKernelEx(&cfg, tri_subst_kernel<T, false>, sp))); }
     ctx->launches++;
-    NLA_CUDA(ctx, cudaGetLastError());
     return NLA_OK;
   }
   if (!P.right) {
@@ -1958,3 +1963,5 @@ int nla_rectrxm_hostb_gated(nla_handle_t h, char side, char uplo, char trans, ch
 }
 
 }  // extern "C"
+
+#include "nla_mg.cuh"

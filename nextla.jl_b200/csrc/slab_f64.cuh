@@ -26,8 +26,11 @@ constexpr int SL_TILE_BYTES = SL_BM * SL_BK * 8;
 constexpr int SL_STAGE_BYTES = 2 * SL_TILE_BYTES;
 constexpr int SL_CONSUMER_WARPS = 8;
 constexpr int SL_THREADS = (SL_CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (1 active warp)
-constexpr int SL_SCRATCH_BYTES = SL_CONSUMER_WARPS * 8 * 16 * 8;
-constexpr int SL_SMEM_BYTES = SL_STAGES * SL_STAGE_BYTES + SL_SCRATCH_BYTES + 1024;
+constexpr int SL_SCR_PITCH = 9;                                        // doubles per column of a warp's 8 x 16 exchange tile (8 rows + 1 pad)
+constexpr int SL_SCRATCH_BYTES = SL_CONSUMER_WARPS * 16 * SL_SCR_PITCH * 8;
+constexpr int SL_LP_DOUBLES = 16 * 64 + 128;                            // per block row: 16 scaled 8 x 8 micro-blocks + 128 reciprocal diagonals
+constexpr int SL_LP_BYTES = 2 * SL_LP_DOUBLES * 8;                      // double-buffered by block-row parity
+constexpr int SL_SMEM_BYTES = SL_STAGES * SL_STAGE_BYTES + SL_SCRATCH_BYTES + SL_LP_BYTES + 1024;
 
 struct SlabParams {
   int T;                  // order of the diagonal block
@@ -39,6 +42,7 @@ struct SlabParams {
   long long ldb;
   double beta, post;
   int unit;               // 1: unit diagonal (the stored diagonal is not used)
+  unsigned long long* dbg;   // probes only (option tc_dbg): 4 globaltimer stamps per block row from warp 0 of CTA 0
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -50,6 +54,8 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
   __shared__ __align__(8) uint64_t full_bar[SL_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[SL_STAGES];
   __shared__ __align__(8) uint64_t xdone_bar;
+  __shared__ __align__(8) uint64_t lp_full[2];    // scaled micro-blocks of a block row are in shared memory (helper warp -> consumers)
+  __shared__ __align__(8) uint64_t lp_empty[2];   // every consumer warp has finished with them
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
@@ -60,6 +66,10 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
       mbar_init(smem_u32(&empty_bar[s]), SL_CONSUMER_WARPS);
     }
     mbar_init(smem_u32(&xdone_bar), SL_CONSUMER_WARPS);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(smem_u32(&lp_full[b]), 1);
+      mbar_init(smem_u32(&lp_empty[b]), SL_CONSUMER_WARPS);
+    }
     mbar_fence_init();
   }
   __syncthreads();
@@ -118,6 +128,49 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
         }
       }
     }
+    if (SOLVE && warp == SL_CONSUMER_WARPS + 1) {
+      // ===== helper warp: the 8 x 8 diagonal micro-blocks of every block row in the reference's scaled form (src/trsm.jl:15-18,24):
+      // reciprocal diagonal rd_r = 1/d_r and l'_rk = a_rk * rd_r.  They depend on A only, so this otherwise idle warp prepares them one
+      // block row AHEAD of the consumers, straight from global memory into a double-buffered shared array: the global loads and the FP64
+      // divisions never appear in the consumers' dependency chain. =====
+      uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+      double* lp_base = reinterpret_cast<double*>(gen + SL_STAGES * SL_STAGE_BYTES + SL_SCRATCH_BYTES);
+      const int hg = lane >> 2, hq = lane & 3;
+      for (int r = 0; r < nb; r++) {
+        const int i = ASC ? r : nb - 1 - r;
+        if (r >= 2) mbar_wait(smem_u32(&lp_empty[r & 1]), ((r >> 1) - 1) & 1);
+        double* lpw = lp_base + (r & 1) * SL_LP_DOUBLES;
+        const int vr = min(SL_BM, p.T - i * SL_BM);
+        const long long base = (long long)p.off + i * SL_BM;
+#pragma unroll 4
+        for (int mb = 0; mb < 16; mb++) {
+          const int rr = mb * 8 + hg;                        // row inside the block row
+          double v[2];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cc = mb * 8 + 2 * hq + e;              // column inside the block row
+            v[e] = 0.0;
+            if (rr < vr && cc < vr) v[e] = p.A[(base + rr) * p.t_rs + (base + cc) * p.t_cs];
+          }
+          // the diagonal entry of row g sits in lane 4g + (g >> 1), element g & 1
+          const double d0 = __shfl_sync(0xffffffffu, v[0], 4 * hg + (hg >> 1));
+          const double d1 = __shfl_sync(0xffffffffu, v[1], 4 * hg + (hg >> 1));
+          const bool valid = rr < vr;
+          const double d = (valid && !p.unit) ? ((hg & 1) ? d1 : d0) : 1.0;
+          // one reciprocal per row instead of a division per entry (costs <= 1 ulp per scaled entry)
+          const double rd = 1.0 / d;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c8 = 2 * hq + e;
+            const bool dep = LOWER ? (c8 < hg) : (c8 > hg);
+            lpw[mb * 64 + hg * 8 + c8] = (valid && dep) ? v[e] * rd : 0.0;
+          }
+          if (hq == 0) lpw[16 * 64 + rr] = valid ? rd : 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&lp_full[r & 1]));
+      }
+    }
     return;
   }
 
@@ -137,12 +190,15 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
     boff[st] = SL_TILE_BYTES + s2 * (SL_W * 64u) + sw64(warp * 16 + g, ki);  // + jn*512
   }
   constexpr uint32_t ASTR = (AMAJ == MAJ_MN) ? 1024u : 512u;
-  double* scratch = reinterpret_cast<double*>(smem_gen + SL_STAGES * SL_STAGE_BYTES) + warp * 128;
+  double* scratch = reinterpret_cast<double*>(smem_gen + SL_STAGES * SL_STAGE_BYTES) + warp * (16 * SL_SCR_PITCH);
+  double* lp_all = reinterpret_cast<double*>(smem_gen + SL_STAGES * SL_STAGE_BYTES + SL_SCRATCH_BYTES);
 
+#define NLA_SLAB_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[(slot)] = global_timer_ns(); } while (0)
   double acc[16][2][2];
   int kt = 0;
   for (int r = 0; r < nb; r++) {
     const int i = ASC ? r : nb - 1 - r;
+    NLA_SLAB_STAMP(4 * r);
 #pragma unroll
     for (int a = 0; a < 16; a++)
 #pragma unroll
@@ -188,6 +244,7 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
     }
 
     // ===== block-row epilogue =====
+    NLA_SLAB_STAMP(4 * r + 1);
     const int rbase = i * SL_BM;                 // block-local row offset inside the diagonal block
     const int vrows = min(SL_BM, p.T - rbase);   // valid rows of this block row
     double* Bblk = p.B + (long long)(p.off + rbase);
@@ -214,106 +271,100 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
       // each holds two 8-row micro-blocks.  The loops stay rolled (code size); accumulator fragments are picked with
       // warp-uniform predicates over statically indexed registers so that `acc` never leaves the register file.
       const int ndt = ktiles(i);
-#pragma unroll 1
-      for (int tt = 0; tt < ndt; tt++, kt++) {
-        const int tc = LOWER ? tt : ndt - 1 - tt;      // 16-column tile of the diagonal block
-        const int s = kt % SL_STAGES;
-        mbar_wait(smem_u32(&full_bar[s]), (kt / SL_STAGES) & 1);
-        const uint32_t sbase = smem_base + s * SL_STAGE_BYTES;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; hh++) {
-          const int s2 = LOWER ? hh : 1 - hh;          // which 8 columns of the tile
-          const int ib = tc * 2 + s2;                  // micro-block = row-block index inside the 128 tile
-          const int mr = ib * 8;
-          const bool valid = (mr + (int)g) < vrows;
-          // row g of the 8x8 diagonal micro-block, from the staged tile (zero beyond the matrix edge)
-          double lrow[8];
+      const double* lpr = lp_all + (r & 1) * SL_LP_DOUBLES;
+      mbar_wait(smem_u32(&lp_full[r & 1]), (r >> 1) & 1);   // the helper warp has this block row's scaled micro-blocks in shared memory
+      // In-register triangular solve of the 128 x 128 diagonal tile.  16-column tiles of it arrive through the ring (ascending for a
+      // lower, descending for an upper triangle); each holds two 8-row micro-blocks.  The 16 micro-block steps are FULLY UNROLLED: the
+      // micro-block index is a compile-time constant, so its accumulator fragments are named registers and the trailing update is
+      // straight-line code.  (A rolled loop has to pick fragments with predicates, and predicated-off DMMAs still occupy the FP64
+      // tensor pipe: measured, every micro-block then pays for all 15 row-blocks.)
 #pragma unroll
-          for (int pp = 0; pp < 8; pp++) {
-            const uint32_t o = (AMAJ == MAJ_MN) ? ((uint32_t)ib * 1024u + sw64(8u * s2 + pp, g))
-                                                : ((uint32_t)s2 * (SL_BM * 64u) + sw64((uint32_t)ib * 8u + g, pp));
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lrow[pp]) : "r"(sbase + o));
-          }
-          double d = 1.0;
+      for (int tcu = 0; tcu < SL_BM / SL_BK; tcu++) {
+        constexpr int NT = SL_BM / SL_BK;
+        const int tc = LOWER ? tcu : NT - 1 - tcu;     // 16-column tile of the diagonal block (compile-time)
+        if (tc < ndt) {                                 // ragged last block row: tiles beyond the matrix edge do not exist
+          const int s = kt % SL_STAGES;
+          mbar_wait(smem_u32(&full_bar[s]), (kt / SL_STAGES) & 1);
+          const uint32_t sbase = smem_base + s * SL_STAGE_BYTES;
 #pragma unroll
-          for (int pp = 0; pp < 8; pp++) if (pp == (int)g && valid && !p.unit) d = lrow[pp];
-          // the reference scales every entry of a row by its diagonal (src/trsm.jl:15-18,24); one reciprocal per row
-          // instead of 12 divisions keeps the FP64 pipe for the DMMAs (costs <= 1 ulp per scaled entry)
-          const double rd = 1.0 / d;
-          double lp[8];
-#pragma unroll
-          for (int pp = 0; pp < 8; pp++) {
-            const bool dep = LOWER ? (pp < (int)g) : (pp > (int)g);
-            lp[pp] = (valid && dep) ? lrow[pp] * rd : 0.0;
-          }
-          double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#define NLA_GET(XX) case XX: x[0][0] = acc[XX][0][0]; x[0][1] = acc[XX][0][1]; x[1][0] = acc[XX][1][0]; x[1][1] = acc[XX][1][1]; break;
-          switch (ib) {   // warp-uniform: one taken case instead of 16 predicated copies
-            NLA_GET(0) NLA_GET(1) NLA_GET(2) NLA_GET(3) NLA_GET(4) NLA_GET(5) NLA_GET(6) NLA_GET(7)
-            NLA_GET(8) NLA_GET(9) NLA_GET(10) NLA_GET(11) NLA_GET(12) NLA_GET(13) NLA_GET(14) NLA_GET(15)
-          }
-#undef NLA_GET
-#pragma unroll
-          for (int y = 0; y < 2; y++)
-#pragma unroll
-            for (int c = 0; c < 2; c++) x[y][c] = valid ? x[y][c] * rd : 0.0;
-          // warp-shuffle substitution: pivot row pv lives in the lanes with g == pv
-#pragma unroll
-          for (int pp = 0; pp < 8; pp++) {
-            const int pv = LOWER ? pp : 7 - pp;
-            const double l = lp[pv];
+          for (int hh = 0; hh < 2; hh++) {
+            const int s2 = LOWER ? hh : 1 - hh;        // which 8 columns of the tile
+            const int ib = tc * 2 + s2;                // micro-block = row-block index inside the 128 tile (compile-time)
+            // The 8 x 16 right-hand-side micro-block goes through the warp's exchange tile (column-major, pitch 9): lane c < 16 then
+            // owns all 8 rows of vector c and runs the substitution of the reference's leaf (src/trsm.jl:15-27: x_r = b_r/d_r -
+            // sum l'_rk x_k, pivots in order) in its own registers -- 28 FMAs, a dependent chain of 7 -- instead of 8 shuffle rounds.
+            __syncwarp();
 #pragma unroll
             for (int y = 0; y < 2; y++)
 #pragma unroll
-              for (int c = 0; c < 2; c++) {
-                const double xp = __shfl_sync(0xffffffffu, x[y][c], 4 * pv + (int)q);
-                x[y][c] = fma(-l, xp, x[y][c]);
+              for (int c = 0; c < 2; c++) scratch[(y * 8 + 2 * (int)q + c) * SL_SCR_PITCH + (int)g] = acc[ib][y][c];
+            __syncwarp();
+            if (lane < 16) {
+              const double* lm = lpr + ib * 64;
+              const double* rv = lpr + 16 * 64 + ib * 8;
+              double* col = scratch + lane * SL_SCR_PITCH;
+              double b[8];
+#pragma unroll
+              for (int rr = 0; rr < 8; rr++) b[rr] = col[rr] * rv[rr];
+#pragma unroll
+              for (int pp = 0; pp < 8; pp++) {
+                const int pv = LOWER ? pp : 7 - pp;    // pivot
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++)
+                  if (LOWER ? (rr > pv) : (rr < pv)) b[rr] = fma(-lm[rr * 8 + pv], b[pv], b[rr]);
               }
-          }
-#define NLA_PUT(XX) case XX: acc[XX][0][0] = x[0][0]; acc[XX][0][1] = x[0][1]; acc[XX][1][0] = x[1][0]; acc[XX][1][1] = x[1][1]; break;
-          switch (ib) {
-            NLA_PUT(0) NLA_PUT(1) NLA_PUT(2) NLA_PUT(3) NLA_PUT(4) NLA_PUT(5) NLA_PUT(6) NLA_PUT(7)
-            NLA_PUT(8) NLA_PUT(9) NLA_PUT(10) NLA_PUT(11) NLA_PUT(12) NLA_PUT(13) NLA_PUT(14) NLA_PUT(15)
-          }
-#undef NLA_PUT
-
-          // X_ib (8 x 16, accumulator layout) -> B fragments (k permuted like the main loop) via the warp's scratch
-          __syncwarp();
 #pragma unroll
-          for (int y = 0; y < 2; y++)
+              for (int rr = 0; rr < 8; rr++) col[rr] = b[rr];
+            }
+            __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 2; c++) scratch[g * 16 + y * 8 + 2 * q + c] = x[y][c];
-          __syncwarp();
-          double bf[2][2];
+            for (int y = 0; y < 2; y++)
 #pragma unroll
-          for (int y = 0; y < 2; y++)
+              for (int c = 0; c < 2; c++) acc[ib][y][c] = scratch[(y * 8 + 2 * (int)q + c) * SL_SCR_PITCH + (int)g];
+            // X_ib as B fragments (k permuted like the main loop)
+            double bf[2][2];
 #pragma unroll
-            for (int s1 = 0; s1 < 2; s1++) bf[y][s1] = scratch[((q & 1) + 4 * (q >> 1) + 2 * s1) * 16 + y * 8 + g];
-          // rows still to be solved: rhs -= Teff[row-block, micro-block] * X_ib, A fragments from the staged tile
-          const uint32_t ao0 = s2 ? aoff[2] : aoff[0], ao1 = s2 ? aoff[3] : aoff[1];
+            for (int y = 0; y < 2; y++)
 #pragma unroll
-          for (int xo = 0; xo < 16; xo++) {
-            const int xx = LOWER ? xo : 15 - xo;
-            const bool after = LOWER ? (xx > ib) : (xx < ib);
-            if (after) {
-              double a0, a1;
-              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"(sbase + ao0 + xx * ASTR));
-              asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a1) : "r"(sbase + ao1 + xx * ASTR));
-              a0 = -a0; a1 = -a1;
+              for (int s1 = 0; s1 < 2; s1++) bf[y][s1] = scratch[(y * 8 + (int)g) * SL_SCR_PITCH + (q & 1) + 4 * (q >> 1) + 2 * s1];
+            // rows still to be solved: rhs -= Teff[row-block, micro-block] * X_ib, A fragments from the staged tile, four row-blocks
+            // at a time (loads first, then their 8 independent DMMAs); the second k-half follows a whole pass later, so the two DMMAs
+            // that hit the same accumulator are never back to back
+            const int NTR = LOWER ? 15 - ib : ib;      // row-blocks still to be updated (a constant once the loops are unrolled)
 #pragma unroll
-              for (int y = 0; y < 2; y++) {
-                dmma884(acc[xx][y][0], acc[xx][y][1], a0, bf[y][0]);
-                dmma884(acc[xx][y][0], acc[xx][y][1], a1, bf[y][1]);
+            for (int s1 = 0; s1 < 2; s1++) {
+              const uint32_t ao = s2 ? aoff[2 + s1] : aoff[s1];
+#pragma unroll
+              for (int t0 = 0; t0 < 16; t0 += 4) {
+                double av[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                  if (t0 + u < NTR) {
+                    const int xx = LOWER ? ib + 1 + t0 + u : ib - 1 - t0 - u;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(av[u]) : "r"(sbase + ao + xx * ASTR));
+                    av[u] = -av[u];
+                  }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                  if (t0 + u < NTR) {
+                    const int xx = LOWER ? ib + 1 + t0 + u : ib - 1 - t0 - u;
+                    dmma884(acc[xx][0][0], acc[xx][0][1], av[u], bf[0][s1]);
+                    dmma884(acc[xx][1][0], acc[xx][1][1], av[u], bf[1][s1]);
+                  }
               }
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+          kt++;
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&lp_empty[r & 1]));
     }
 
     // write the block row back in place
+    NLA_SLAB_STAMP(4 * r + 2);
 #pragma unroll
     for (int y = 0; y < 2; y++)
 #pragma unroll
@@ -338,7 +389,9 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&xdone_bar));
     }
+    NLA_SLAB_STAMP(4 * r + 3);
   }
+#undef NLA_SLAB_STAMP
 }
 
 }  // namespace nla

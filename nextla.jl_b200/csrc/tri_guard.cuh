@@ -86,6 +86,10 @@ struct TriSubstParams {
 
 template <typename T, bool LOWER>
 __global__ void __launch_bounds__(TS_THREADS) tri_subst_kernel(const TriSubstParams<T> p) {
+  // launched with programmatic dependent launch: the successor's prologue may start at once, and this kernel waits here for the leaf
+  // GEMM in front of it (whose own wait covered everything before), so that an unused fallback costs a few microseconds, not a drain
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (!tri_cond_bad(p.rec, p.thr2)) return;
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.counter) atomicAdd(p.counter, 1.0);
   __shared__ __align__(16) float Ts[TS_KC][TS_RB];   // Ts[j][i] = Teff(r0 + i, k0 + j): one float4 x 4 per k for the 16 rows

@@ -27,8 +27,10 @@ def test_library_exports_every_declared_symbol(nla):
 
 def test_status_strings_and_invalid_handle(nla):
     lib = nla.load_library()
-    for code in range(0, 9):
-        assert lib.nla_status_string(code)
+    for code in range(0, 11):
+        assert lib.nla_status_string(code) and b"unknown" not in lib.nla_status_string(code)
+    assert lib.nla_mg_destroy(None) == 8 and lib.nla_mg_sync(None) == 8 and lib.nla_mg_device_count(None) == -1
+    assert lib.nla_workspace_bytes(None, b"L", b"S", 1, 1024, 1024) == -8
     assert lib.nla_destroy(None) == 8
     assert lib.nla_rectrxm(None, b"L", b"L", b"N", b"S", 0, 4, 4, 1.0, None, 4, None, 4, None) == 8
     assert lib.nla_leaf_max(0) == 128 and lib.nla_leaf_max(7) == -1
@@ -44,6 +46,8 @@ def test_create_without_gpu_fails_loudly(nla):
     assert rc == 6 and not h.value  # NLA_ERR_NO_DEVICE: no CPU fallback
     with pytest.raises(nla.NextLAError):
         nla.Handle(0)
+    mg = ctypes.c_void_p()
+    assert nla.load_library().nla_mg_create(ctypes.byref(mg), 1, None) == 6 and not mg.value
 
 
 def test_product_never_imports_oracle():

@@ -149,3 +149,46 @@ def test_wrong_device_handle_is_rejected(nla, gpu):
         assert np.allclose(nla.to_numpy(B1), 2.0)
     finally:
         h1.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float16])
+def test_single_process_multi_gpu_entry(nla, gpu, dtype):
+    """nla_mg_* (SURVEY.md 8(b)): the library-owned multi-GPU pipeline -- NCCL communicator, per-GPU streams, panel broadcast of A,
+    gated solves -- driven from one host thread through ctypes, no torch.distributed.  Uses every GPU of the box (1 here on a
+    one-GPU box: same code path minus the NCCL calls; `gpurun --gpus 2` runs it with a real broadcast).  Device-resident and
+    host-buffer variants against the single-GPU call, ragged shards, an empty shard, a non-zero root."""
+    import torch
+
+    ng = torch.cuda.device_count()
+    tol = 1e-13 if dtype == np.float64 else 1e-2
+    mg = nla.MultiGPU(ngpu=ng)
+    try:
+        n = 2304
+        per = [300 + 136 * i for i in range(ng)]
+        if ng > 1:
+            per[-1] = 0                                    # an empty shard must be harmless
+        root = ng - 1
+        for side, uplo, trans, func in [("L", "L", "N", "S"), ("R", "U", "T", "S"), ("L", "U", "N", "M"), ("R", "L", "N", "M")]:
+            m = sum(per)
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=50, recipe="scaled")
+            want = _run(nla, None, side, uplo, trans, 1.25, func, A, B0)
+            offs = np.cumsum([0] + per)
+            parts = [np.asfortranarray(B0[:, offs[i]:offs[i + 1]] if side == "L" else B0[offs[i]:offs[i + 1], :]) for i in range(ng)]
+            # device-resident
+            dA = nla.colmajor(A, device=f"cuda:{root}")
+            shards = [nla.colmajor(parts[i], device=f"cuda:{i}") for i in range(ng)]
+            for d in range(ng):
+                torch.cuda.synchronize(d)
+            mg.rectrxm(side, uplo, trans, 1.25, func, dA, root, shards)
+            mg.sync()
+            got = np.concatenate([nla.to_numpy(s) for s in shards], axis=1 if side == "L" else 0)
+            assert np.array_equal(got, want) or rp.error_metric(side, uplo, trans, 1.25, func, A, B0, got) < tol, (side, uplo, trans, func)
+            assert rp.error_metric(side, uplo, trans, 1.25, func, A, B0, got) < tol
+            # host buffers
+            hparts = [p.copy(order="F") for p in parts]
+            mg.rectrxm_host(side, uplo, trans, 1.25, func, A, hparts)
+            got = np.concatenate(hparts, axis=1 if side == "L" else 0)
+            assert rp.error_metric(side, uplo, trans, 1.25, func, A, B0, got) < tol, (side, uplo, trans, func)
+        assert torch.cuda.current_device() == 0
+    finally:
+        mg.close()

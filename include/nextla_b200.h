@@ -137,6 +137,14 @@ int nla_memcpy2d_async(nla_handle_t handle, void *dst, int64_t dst_pitch_bytes, 
 int nla_laswp(nla_handle_t handle, int dtype, int64_t rows, int64_t ncols, void *A, int64_t lda, int64_t k1, int64_t k2,
               const int64_t *ipiv, int incx, void *stream);
 
+/* lauum!(uplo, n, A, ib)                                                                 -- src/lauum.jl:52-186
+ * A := L^H * L (uplo 'L') or U * U^H (uplo 'U') on a device matrix: the triangular factor is stored in the `uplo` triangle of A, the
+ * result replaces it in the same triangle; the opposite triangle is neither used nor written (the reference multiplies whole diagonal
+ * blocks, i.e. assumes it holds zeros).  Block loop of the reference (compute_lower! / compute_upper!) with the off-diagonal steps on the
+ * trmm / GEMM kernels of this library and the diagonal-block products through GEMMs whose epilogue stores only the `uplo` triangle.
+ * ib <= 0: 1024.  The reference throws ArgumentError for a bad uplo or negative n (:54-60): NLA_ERR_INVALID_CHAR / NLA_ERR_INVALID_DIM. */
+int nla_lauum(nla_handle_t handle, char uplo, int dtype, int64_t n, void *A, int64_t lda, int64_t ib, void *stream);
+
 /* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
  * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
  * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */

@@ -55,6 +55,7 @@ def load_library():
         "nla_last_cuda_error": (I, [H]),
         "nla_version": (I, []),
         "nla_probe_fp64_peak": (I, [H, c.POINTER(c.c_double)]),
+        "nla_lauum": (I, [H, CH, I, L, P, L, L, P]),
         "nla_mg_create": (I, [c.POINTER(H), I, c.POINTER(c.c_int)]),
         "nla_mg_destroy": (I, [H]),
         "nla_mg_device_count": (I, [H]),
@@ -96,7 +97,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak",
+            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak", "nla_lauum",
             "nla_mg_create", "nla_mg_destroy", "nla_mg_device_count", "nla_mg_handle", "nla_mg_stream", "nla_mg_last_nccl_error", "nla_mg_sync",
             "nla_mg_rectrxm", "nla_mg_rectrxm_host",
             "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
@@ -419,46 +420,16 @@ def getrf2_update(A, n1: int, ipiv, **kw):
     return A
 
 
-def lauum(uplo: str, A, ib: int = 1024, **kw):
+def lauum(uplo: str, A, ib: int = 1024, stream=None, handle: Optional[Handle] = None):
     """lauum!(uplo, n, A, ib) -- src/lauum.jl:52-186: A := L^H * L (uplo 'L') or U * U^H (uplo 'U'), the triangular factor stored in
     the `uplo` triangle of the device matrix A, result in the same triangle; the opposite triangle is neither read nor written
-    (the reference multiplies the full diagonal blocks, i.e. assumes it is zero).  Block loop of the reference with its O(n^3) steps
-    on this library's kernels: the off-diagonal block row/column through trmm (nla_trxm) and GEMM_ADD (nla_gemm_update); the
-    ib x ib diagonal blocks through trmm / GEMM_ADD into a scratch block whose triangle is merged back with torch.tril / triu
-    (SURVEY.md 8(f3))."""
-    import torch
-
-    n = A.shape[0]
-    if uplo not in ("L", "U"):
-        raise NextLAError("uplo must be 'L' or 'U'")          # src/lauum.jl:54
-    if A.shape[1] != n:
+    (the reference multiplies the full diagonal blocks, i.e. assumes it is zero).  One call into the library (nla_lauum): the block
+    loop, the trmm / GEMM steps and the triangle-masked diagonal-block products all run there."""
+    h = _handle_for(handle, A, stream)
+    pa, rows, cols, lda, dta = _desc(A)
+    if rows != cols:
         raise NextLAError("A must be square")
-    lower = uplo == "L"
-    tri, anti = (torch.tril, torch.triu) if lower else (torch.triu, torch.tril)
-    for i0 in range(0, n, ib):
-        b = min(ib, n - i0)
-        i1 = i0 + b
-        Aii = A[i0:i1, i0:i1]
-        tmp = torch.zeros((b, b), dtype=A.dtype, device=A.device).t()      # column-major scratch
-        if lower:
-            if i0 > 0:
-                trmm("L", "L", "T", "N", Aii, A[i0:i1, :i0], 1.0, **kw)     # A[i, :i0] = L_ii^H A[i, :i0]              (:165)
-            tmp.copy_(tri(Aii))
-            trmm("L", "L", "T", "N", Aii, tmp, 1.0, **kw)                   # L_ii^H L_ii                                (:169-172)
-            if i1 < n:
-                if i0 > 0:
-                    GEMM_ADD(A[i1:, i0:i1], A[i1:, :i0], A[i0:i1, :i0], transa="T", **kw)   # += A[i1:, i]^H A[i1:, :i0]   (:177)
-                GEMM_ADD(A[i1:, i0:i1], A[i1:, i0:i1], tmp, transa="T", **kw)               # rank-k update of the block    (:180-183)
-        else:
-            if i0 > 0:
-                trmm("R", "U", "T", "N", Aii, A[:i0, i0:i1], 1.0, **kw)     # A[:i0, i] = A[:i0, i] U_ii^H              (:110)
-            tmp.copy_(tri(Aii))
-            trmm("R", "U", "T", "N", Aii, tmp, 1.0, **kw)                   # U_ii U_ii^H                                (:114-118)
-            if i1 < n:
-                if i0 > 0:
-                    GEMM_ADD(A[:i0, i1:], A[i0:i1, i1:], A[:i0, i0:i1], transb="T", **kw)   # += A[:i0, i1:] A[i, i1:]^H   (:124)
-                GEMM_ADD(A[i0:i1, i1:], A[i0:i1, i1:], tmp, transb="T", **kw)               # rank-k update                (:127-131)
-        Aii.copy_(tri(tmp) + anti(Aii, 1 if lower else -1))
+    _check(load_library().nla_lauum(h._h, _ch(uplo), dta, rows, pa, lda, int(ib), _stream_ptr(stream, h.device)), h._h)
     return A
 
 

@@ -39,6 +39,8 @@ struct GemmF64Params {
   long long ldc;
   double beta, sgn, post;
   int tiles_m, tiles_n;
+  int tri_mode;    // 0: whole block; 1 / 2: only the lower / upper triangle (diagonal included) of C is read and written (nla_lauum)
+  int overwrite;   // 1: C <- post * sgn * A*B (old contents not read)
 };
 
 // byte offset of element (outer index `o`, inner index 0..7 `e`) inside one 64B-swizzled block-of-8 panel:
@@ -154,7 +156,8 @@ gemm_f64_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int row = row0 + i * 8;
-          if (row < p.M) {
+          if (row < p.M && !(p.tri_mode == 1 ? row < col : (p.tri_mode == 2 && row > col))) {
+            if (p.overwrite) { cp[row] = __dmul_rn(p.post, p.sgn * acc[i][j][c]); continue; }
             double v = cp[row];
             if (unit) {
               v = v + p.sgn * acc[i][j][c];

@@ -16,6 +16,8 @@ struct GemmSimtParams {
   const T* B; long long b_rs, b_cs;   // B(k,j) = B[k*b_rs + j*b_cs]
   T* C; long long ldc;                // column-major output
   double beta, sgn, post;
+  int tri_mode;    // 0: whole block; 1 / 2: only the lower / upper triangle (diagonal included) of C is READ AND WRITTEN (nla_lauum)
+  int overwrite;   // 1: C <- post * sgn * A*B (old contents not read)
 };
 
 constexpr int GS_BM = 64, GS_BN = 64, GS_BK = 16, GS_THREADS = 256;
@@ -71,7 +73,9 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_simt_kernel(const GemmSimtPar
     for (int i = 0; i < 4; i++) {
       const int row = m0 + tx * 4 + i;
       if (row >= p.M) continue;
+      if (p.tri_mode == 1 ? row < col : (p.tri_mode == 2 && row > col)) continue;
       T* cp = p.C + (long long)col * p.ldc + row;
+      if (p.overwrite) { Traits<T>::st(cp, (Acc)(p.post * p.sgn * (double)acc[i][j])); continue; }
       // mirror the reference's rounding points: scale rounded to T, update evaluated in Float64 and
       // rounded once (src/matmul.jl:64), final scale rounded to T (src/rectrxm.jl:64,72)
       double v = (double)Traits<T>::ld(cp);

@@ -91,11 +91,14 @@ struct GemmTcParams {
   // conditioning guard of a block-inverse leaf (tri_guard.cuh): when the record says the block is ill-conditioned the launch does
   // nothing and the substitution kernel launched right behind it solves the block instead
   const double* skip_rec; double skip_thr2;
+  // 0: whole block; 1 / 2: only the lower / upper triangle (diagonal included) of C is written (nla_lauum's diagonal blocks; one-tile kernel only)
+  int tri_mode;
 };
 
+// evaluated AFTER griddepcontrol.wait (the record is written by a predecessor on the stream, or on a side stream joined by an event);
+// uniform for the whole grid.  A skipped launch runs its prologue and teardown with zero K steps / zero tiles.
 __device__ __forceinline__ bool tc_skip_launch(const GemmTcParams& p) {
   if (!p.skip_rec) return false;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // the record is written by a predecessor on the stream (or a side stream joined by an event)
   const double r0 = p.skip_rec[0], r1 = p.skip_rec[1], r2 = p.skip_rec[2];
   return r2 > 0.0 || !(r0 * r1 <= p.skip_thr2);
 }
@@ -137,8 +140,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __shared__ uint32_t tmem_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-
-  if (tc_skip_launch(p)) return;   // uniform for the grid; nothing allocated yet
 
   // grouped rasterisation: CTAs resident together share A row panels / B column panels in L2
   const int per_group = TC_GROUP_M * p.tiles_n;
@@ -201,11 +202,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) NLA_STAMP(1);   // prologue done (barriers, TMEM, dependency wait)
   const uint32_t tmem = tmem_slot;
-  const int nk = (klen + BK - 1) / BK;
+  const int nk = tc_skip_launch(p) ? 0 : (klen + BK - 1) / BK;   // conditioning guard: a rejected block-inverse leaf does nothing
   // K is accumulated in TMEM in chunks; each finished chunk is added to C in registers with round-to-nearest by the drain
   // warps while the next chunk runs into the other TMEM tile.  The tensor core's own accumulation truncates, which biases
   // long same-sign sums (measured ~2^-24 relative per MMA); chunking bounds that for Float32.  Float16 uses one chunk.
-  const int chunk_kb = (NBUF > 1 && p.chunk_k > 0) ? max(1, p.chunk_k / BK) : nk;
+  const int chunk_kb = (NBUF > 1 && p.chunk_k > 0) ? max(1, p.chunk_k / BK) : max(1, nk);
   const int nchunks = (nk + chunk_kb - 1) / chunk_kb;
 
   if (warp == 0) {
@@ -391,11 +392,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               outv[e] = tc_from_float<T>(post * tc_to_float<T>(tc_from_float<T>(v)));
             }
             T* dst = cbase + grow + (long long)(tn * BN + col) * p.ldc;
-            if (grow + VEC <= p.M) {
+            const int gcol = tn * BN + col;
+            // triangle-masked store: rows [grow, grow + VEC) of column gcol against the diagonal of the output block
+            const bool tri_all = p.tri_mode == 0 || (p.tri_mode == 1 ? grow >= gcol : grow + VEC - 1 <= gcol);
+            const bool tri_none = p.tri_mode != 0 && (p.tri_mode == 1 ? grow + VEC - 1 < gcol : grow > gcol);
+            if (tri_none) {
+            } else if (grow + VEC <= p.M && tri_all) {
               *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outv);
             } else {
 #pragma unroll
-              for (int e = 0; e < VEC; e++) if (grow + e < p.M) dst[e] = outv[e];
+              for (int e = 0; e < VEC; e++)
+                if (grow + e < p.M && (p.tri_mode == 0 || (p.tri_mode == 1 ? grow + e >= gcol : grow + e <= gcol))) dst[e] = outv[e];
             }
             if (last && p.dup) {   // second copy of the rows/columns the next block-inverse leaf reads (its GEMM is out of place)
               const int dr = grow - p.dup_r0, dc = tn * BN + col - p.dup_c0;

@@ -105,12 +105,10 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  if (tc_skip_launch(p)) return;   // uniform for the grid (both CTAs of every pair); nothing allocated, no cluster barrier passed yet
-
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pairs_m = (p.tiles_m + 1) >> 1;
-  const int ntiles = pairs_m * p.tiles_n;
+  int ntiles = pairs_m * p.tiles_n;
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -136,6 +134,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated in both SMs
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tc_skip_launch(p)) ntiles = 0;   // conditioning guard: a rejected block-inverse leaf walks an empty tile list (uniform for the grid)
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) NLA_STAMP3(1);
 

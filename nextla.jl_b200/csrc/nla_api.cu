@@ -86,6 +86,7 @@ struct nla_context {
   int64_t inv_guard_kappa;   // threshold override of the guard (0 = default per element type)
   int64_t cond_blocks;       // number of records the last guarded solve wrote (nla_get_option "inv_fallbacks" reads them back)
   int64_t nvtx;         // 1 = NVTX ranges around calls and schedule ops
+  void* lauum_ws; size_t lauum_ws_bytes;   // one masked diagonal block (nla_lauum)
 };
 
 static const uint32_t NLA_MAGIC = 0x4e4c4142u;  // "NLAB"
@@ -228,8 +229,10 @@ static int launch_leaf(nla_context* ctx, const Problem& P, const Op& o, int64_t 
 // generic strided GEMM: C(MxN) <- post*(beta*C + sgn*A*B)
 template <typename T>
 static int launch_gemm_simt(nla_context* ctx, int64_t M, int64_t N, int64_t K, const T* A, int64_t a_rs, int64_t a_cs, const T* B,
-                            int64_t b_rs, int64_t b_cs, T* C, int64_t ldc, double beta, double sgn, double post, cudaStream_t st) {
+                            int64_t b_rs, int64_t b_cs, T* C, int64_t ldc, double beta, double sgn, double post, cudaStream_t st,
+                            int tri_mode = 0, int overwrite = 0) {
   GemmSimtParams<T> gp;
+  gp.tri_mode = tri_mode; gp.overwrite = overwrite;
   gp.M = (int)M; gp.N = (int)N; gp.K = (int)K;
   gp.A = A; gp.a_rs = a_rs; gp.a_cs = a_cs;
   gp.B = B; gp.b_rs = b_rs; gp.b_cs = b_cs;
@@ -409,7 +412,7 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
   if constexpr (sizeof(T) == 2) {
     // Float16, long updates: 256 x 512 pair tiles (two accumulators share the A tile: 171 instead of 128 flop per byte of L2 traffic)
     if (ctx->tc_wide_k > 0 && gp.win_mode == 0 && gp.K >= ctx->tc_wide_k && gp.M >= 256 && gp.N >= 512 && !force_bn && ctx->tc_bn == 0 &&
-        ctx->tc_cg != 1) {
+        ctx->tc_cg != 1 && gp.tri_mode == 0) {
       gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + 511) / 512;
       if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc4_variant<MAJ_MN, MAJ_K>(ctx, mA, mB128, gp, st);
       if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc4_variant<MAJ_K, MAJ_K>(ctx, mA, mB128, gp, st);
@@ -421,14 +424,14 @@ static int launch_gemm_tc(nla_context* ctx, int amaj, int bmaj, const CUtensorMa
     // (measured on B200, N = 16384: M = K = 1024 545 vs 503 TFLOP/s, 2048 1042 vs 875, 4096 equal; from K = 8192 on the one-tile pair
     //  kernel with two CTAs per SM wins by 4-6 %, so the long updates stay there; option tc_persist = 2 forces the persistent kernel)
     const bool long_k = gp.win_mode == 0 && gp.K >= 8192 && ctx->tc_persist != 2 && tc_pick_pair<T>(ctx, gp);
-    if (ctx->tc_persist && !long_k && win_ok && gp.M > TC_BM && (!force_bn || gp.win_mode != 0) && ctx->tc_bn == 0 && ctx->tc_cg != 1) {
+    if (ctx->tc_persist && !long_k && win_ok && gp.M > TC_BM && (!force_bn || gp.win_mode != 0) && ctx->tc_bn == 0 && ctx->tc_cg != 1 && gp.tri_mode == 0) {
       gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + 255) / 256;
       if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc3_variant<MAJ_MN, MAJ_K>(ctx, mA, mB128, gp, st);
       if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc3_variant<MAJ_K, MAJ_K>(ctx, mA, mB128, gp, st);
       if (amaj == MAJ_MN && bmaj == MAJ_MN) return launch_gemm_tc3_variant<MAJ_MN, MAJ_MN>(ctx, mA, mB128, gp, st);
     }
   }
-  if (!force_bn && tc_pick_pair<T>(ctx, gp)) {
+  if (!force_bn && gp.tri_mode == 0 && tc_pick_pair<T>(ctx, gp)) {
     gp.tiles_m = (gp.M + TC_BM - 1) / TC_BM; gp.tiles_n = (gp.N + 255) / 256;
     if (amaj == MAJ_MN && bmaj == MAJ_K) return launch_gemm_tc2_variant<T, MAJ_MN, MAJ_K>(ctx, mA, mB128, gp, st);
     if (amaj == MAJ_K && bmaj == MAJ_K) return launch_gemm_tc2_variant<T, MAJ_K, MAJ_K>(ctx, mA, mB128, gp, st);
@@ -1244,7 +1247,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0;
+  ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1270,6 +1273,7 @@ int nla_destroy(nla_handle_t h) {
   if (h->stage_a) cudaFree(h->stage_a);
   if (h->stage_b) cudaFree(h->stage_b);
   release_ws(h);
+  if (h->lauum_ws) cudaFreeAsync(h->lauum_ws, 0);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
   for (auto e : h->panel_prep_events) cudaEventDestroy(e);
@@ -1588,7 +1592,7 @@ int nla_trmm_leaf(nla_handle_t h, char side, char uplo, int dtype, int64_t n, in
 
 template <typename T>
 static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int64_t N, int64_t K, int sign, const void* A, int64_t lda,
-                             const void* B, int64_t ldb, void* C, int64_t ldc, cudaStream_t st) {
+                             const void* B, int64_t ldb, void* C, int64_t ldc, cudaStream_t st, int tri_mode = 0, int overwrite = 0) {
   const bool at = ta != 'N', bt = tb != 'N';
   if constexpr (!std::is_same<T, double>::value) {
     // tcgen05 path: operands straight from the caller's matrices when they satisfy the TMA constraints
@@ -1600,7 +1604,7 @@ static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int6
           encode_map_tc<T>(ctx, &mB128, B, br, bc, ldb, majB, false, 128)) {
         GemmTcParams gp{};
         gp.M = (int)M; gp.N = (int)N; gp.K = (int)K; gp.C = C; gp.ldc = ldc;
-        gp.beta = 1.f; gp.sgn = (float)sign; gp.post = 1.f; gp.overwrite = 0;
+        gp.beta = overwrite ? 0.f : 1.f; gp.sgn = (float)sign; gp.post = 1.f; gp.overwrite = overwrite; gp.tri_mode = tri_mode;
         return launch_gemm_tc<T>(ctx, majA, majB, mA, mB, mB128, gp, st);
       }
     }
@@ -1614,7 +1618,7 @@ static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int6
       if (encode_map(ctx, &mA, A, ar, ac, lda, majA) && encode_map(ctx, &mB, B, br, bc, ldb, majB)) {
         GemmF64Params gp{};
         gp.M = (int)M; gp.N = (int)N; gp.K = (int)K; gp.C = (double*)C; gp.ldc = ldc;
-        gp.beta = 1.0; gp.sgn = sign; gp.post = 1.0;
+        gp.beta = 1.0; gp.sgn = sign; gp.post = 1.0; gp.tri_mode = tri_mode; gp.overwrite = overwrite;
         gp.tiles_m = (gp.M + GF_BM - 1) / GF_BM; gp.tiles_n = (gp.N + GF_BN - 1) / GF_BN;
         if (!at && !bt) return launch_gemm_f64_tma<MAJ_MN, MAJ_K>(ctx, mA, mB, gp, st);
         if (at && !bt) return launch_gemm_f64_tma<MAJ_K, MAJ_K>(ctx, mA, mB, gp, st);
@@ -1623,7 +1627,79 @@ static int gemm_update_typed(nla_context* ctx, char ta, char tb, int64_t M, int6
     }
   }
   return launch_gemm_simt<T>(ctx, M, N, K, (const T*)A, at ? lda : 1, at ? 1 : lda, (const T*)B, bt ? ldb : 1, bt ? 1 : ldb, (T*)C, ldc,
-                             1.0, (double)sign, 1.0, st);
+                             1.0, (double)sign, 1.0, st, tri_mode, overwrite);
+}
+
+// ---- lauum!(uplo, n, A, ib)  -- src/lauum.jl:52-186 --------------------------------------------------------------------------
+// A := L^H L (uplo 'L') or U U^H (uplo 'U'), the factor in the `uplo` triangle of A, result in the same triangle; the opposite
+// triangle is neither used nor written.  The reference's block loop (compute_lower! :146-186 / compute_upper! :91-129) with every
+// O(n^3) step on this library's kernels:
+//   off-diagonal block row / column   trmm with the diagonal block (rectrxm_typed), then a GEMM update with the trailing panel
+//   diagonal block                    T1 = triangle of the block (masked copy, tri_copy_kernel);  block <- T1^H T1 (or T1 T1^H) and
+//                                     block += trailing^H trailing through GEMMs whose EPILOGUE stores only the `uplo` triangle
+//                                     (GemmF64Params / GemmTcParams / GemmSimtParams::tri_mode): no scratch result, no merge pass.
+template <typename T>
+__global__ void __launch_bounds__(256) tri_copy_kernel(const T* __restrict__ A, long long lda, T* __restrict__ W, long long ldw, int b, int lower) {
+  const long long total = (long long)b * b;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e % b), c = (int)(e / b);
+    const bool in = lower ? (r >= c) : (r <= c);
+    W[r + c * ldw] = in ? A[r + c * lda] : T(0.0f);
+  }
+}
+
+template <typename T>
+static int lauum_typed(nla_context* ctx, bool lower, int64_t n, T* A, int64_t lda, int64_t ib, cudaStream_t st) {
+  const size_t es = sizeof(T);
+  const int dtype = std::is_same<T, double>::value ? NLA_F64 : std::is_same<T, float>::value ? NLA_F32 : NLA_F16;
+  const int64_t ldw = (ib + 15) & ~15ll;
+  {   // scratch for one masked diagonal block, library-owned (stream-ordered allocation)
+    const size_t need = (size_t)ldw * ib * es;
+    if (ctx->lauum_ws_bytes < need) {
+      if (ctx->lauum_ws) NLA_CUDA(ctx, cudaFreeAsync(ctx->lauum_ws, st));
+      ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0;
+      NLA_CUDA(ctx, cudaMallocAsync(&ctx->lauum_ws, need, st));
+      ctx->lauum_ws_bytes = need; ctx->ws_allocs++;
+    }
+  }
+  T* W = (T*)ctx->lauum_ws;
+  for (int64_t i0 = 0; i0 < n; i0 += ib) {
+    const int64_t b = std::min(ib, n - i0), i1 = i0 + b;
+    T* Aii = A + i0 + i0 * lda;
+    int rc;
+    Problem P;
+    if (lower) {
+      if (i0 > 0) {   // A[i, :i0] = L_ii^H A[i, :i0]                                                     (:165)
+        if ((rc = make_problem(P, 'L', 'L', 'T', 'M', dtype, b, i0, 1.0, Aii, lda, A + i0, lda)) != NLA_OK) return rc;
+        if ((rc = rectrxm_typed<T>(ctx, P, st)) != NLA_OK) return rc;
+      }
+    } else {
+      if (i0 > 0) {   // A[:i0, i] = A[:i0, i] U_ii^H                                                     (:110)
+        if ((rc = make_problem(P, 'R', 'U', 'T', 'M', dtype, b, i0, 1.0, Aii, lda, A + i0 * lda, lda)) != NLA_OK) return rc;
+        if ((rc = rectrxm_typed<T>(ctx, P, st)) != NLA_OK) return rc;
+      }
+    }
+    // masked copy of the diagonal block, then the block product straight into the `uplo` triangle of A_ii      (:114-118 / :169-172)
+    const unsigned cgrid = (unsigned)std::min<int64_t>((b * b + 255) / 256, (int64_t)ctx->sm_count * 8);
+    tri_copy_kernel<T><<<cgrid, 256, 0, st>>>(Aii, lda, W, ldw, (int)b, lower ? 1 : 0);
+    ctx->launches++;
+    NLA_CUDA(ctx, cudaGetLastError());
+    if (lower) rc = gemm_update_typed<T>(ctx, 'T', 'N', b, b, b, +1, W, ldw, W, ldw, Aii, lda, st, 1, 1);
+    else rc = gemm_update_typed<T>(ctx, 'N', 'T', b, b, b, +1, W, ldw, W, ldw, Aii, lda, st, 2, 1);
+    if (rc != NLA_OK) return rc;
+    if (i1 < n) {
+      if (lower) {
+        // A[i, :i0] += A[i1:, i]^H A[i1:, :i0]  (:177);   A_ii += A[i1:, i]^H A[i1:, i], lower triangle only  (:180-183)
+        if (i0 > 0 && (rc = gemm_update_typed<T>(ctx, 'T', 'N', b, i0, n - i1, +1, A + i1 + i0 * lda, lda, A + i1, lda, A + i0, lda, st)) != NLA_OK) return rc;
+        if ((rc = gemm_update_typed<T>(ctx, 'T', 'N', b, b, n - i1, +1, A + i1 + i0 * lda, lda, A + i1 + i0 * lda, lda, Aii, lda, st, 1, 0)) != NLA_OK) return rc;
+      } else {
+        // A[:i0, i] += A[:i0, i1:] A[i, i1:]^H  (:124);   A_ii += A[i, i1:] A[i, i1:]^H, upper triangle only  (:127-131)
+        if (i0 > 0 && (rc = gemm_update_typed<T>(ctx, 'N', 'T', i0, b, n - i1, +1, A + i1 * lda, lda, A + i0 + i1 * lda, lda, A + i0 * lda, lda, st)) != NLA_OK) return rc;
+        if ((rc = gemm_update_typed<T>(ctx, 'N', 'T', b, b, n - i1, +1, A + i0 + i1 * lda, lda, A + i0 + i1 * lda, lda, Aii, lda, st, 2, 0)) != NLA_OK) return rc;
+      }
+    }
+  }
+  return NLA_OK;
 }
 
 extern "C" {
@@ -1648,6 +1724,24 @@ int nla_gemm_update(nla_handle_t h, int dtype, char transa, char transb, int64_t
 }
 
 }  // extern "C"
+
+extern "C" int nla_lauum(nla_handle_t h, char uplo, int dtype, int64_t n, void* A, int64_t lda, int64_t ib, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (uplo != 'L' && uplo != 'U') return NLA_ERR_INVALID_CHAR;                     // src/lauum.jl:54
+  if (dtype != NLA_F64 && dtype != NLA_F32 && dtype != NLA_F16) return NLA_ERR_INVALID_DTYPE;
+  if (n < 0 || n >= (1ll << 31) || lda < std::max<int64_t>(1, n)) return NLA_ERR_INVALID_DIM;   // :58
+  if (n == 0) return NLA_OK;                                                       // :63
+  if (!A) return NLA_ERR_NULL_POINTER;
+  if (ib <= 0) ib = 1024;
+  ib = std::max<int64_t>(1, std::min(ib, n));                                      // :68
+  NLA_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case NLA_F64: return lauum_typed<double>(h, uplo == 'L', n, (double*)A, lda, ib, st);
+    case NLA_F32: return lauum_typed<float>(h, uplo == 'L', n, (float*)A, lda, ib, st);
+    default: return lauum_typed<__half>(h, uplo == 'L', n, (__half*)A, lda, ib, st);
+  }
+}
 
 // Host-buffer entry point: the e2e path.  Nothing is staged wholesale: A travels as 1024x1024 tiles of the referenced
 // triangle and B as chunks of 1024 vector elements (row blocks for side 'L', column blocks for side 'R'), queued on one

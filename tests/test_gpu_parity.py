@@ -716,11 +716,13 @@ def test_wide_pair_kernel(nla, gpu):
         gpu.set_option("tc_wide_k", 4096)
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5)])
-@pytest.mark.parametrize("n,ib", [(96, 32), (1000, 256), (2048, 1024)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 1e-5), (np.float16, 1e-2)])
+@pytest.mark.parametrize("n,ib", [(96, 32), (1000, 256), (2048, 1024), (1544, 0), (3072, 1024), (200, 4096)])
 def test_lauum_block_loop(nla, gpu, dtype, tol, n, ib):
-    """lauum! (src/lauum.jl:52-186) as the reference's block loop on this library's trmm / GEMM kernels: L^H L and
-    U U^H against NumPy; the opposite triangle (NaN here) is neither read nor written."""
+    """lauum! (src/lauum.jl:52-186) through ONE C entry (nla_lauum): the reference's block loop with the off-diagonal
+    steps on this library's trmm / GEMM kernels and the diagonal-block products through triangle-masked GEMM epilogues.  L^H L and
+    U U^H against NumPy; the opposite triangle (NaN here) is neither used nor written; ib <= 0 (default 1024), ib > n (one block),
+    ragged last block, a padded leading dimension; bad arguments are status codes (the reference throws ArgumentError, :54-60)."""
     import torch
 
     rng = np.random.RandomState(n + ib)
@@ -730,11 +732,51 @@ def test_lauum_block_loop(nla, gpu, dtype, tol, n, ib):
         want = (T.astype(np.float64).T @ T.astype(np.float64)) if uplo == "L" else (T.astype(np.float64) @ T.astype(np.float64).T)
         Ain = T.copy()
         Ain[np.triu_indices(n, 1) if uplo == "L" else np.tril_indices(n, -1)] = np.nan
-        dA = nla.colmajor(Ain)
+        if n == 1544:   # padded leading dimension
+            dA = nla.empty_colmajor(n, n, getattr(torch, np.dtype(dtype).name), ld=n + 8)
+            dA.copy_(torch.from_numpy(np.ascontiguousarray(Ain)).cuda())
+        else:
+            dA = nla.colmajor(Ain)
+        gpu.launch_count(reset=True)
         nla.lauum(uplo, dA, ib)
         torch.cuda.synchronize()
+        assert gpu.launch_count() > 0
         got = nla.to_numpy(dA)
         mask = np.tril(np.ones((n, n), bool)) if uplo == "L" else np.triu(np.ones((n, n), bool))
         assert np.isnan(got[~mask]).all()                       # untouched
         assert np.isfinite(got[mask]).all()
-        assert np.linalg.norm(got[mask] - want[mask]) / np.linalg.norm(want[mask]) < tol, uplo
+        # Float32: the diagonal of L^H L is a large term plus many small same-sign ones -- the worst case for the tensor core's
+        # truncating accumulation (~2^-24 per MMA, one direction), hence 3e-5 on the relative error here; the reference's
+        # own criterion for lauum (test/lauum.jl:26: ||A - expected||_F / n < 1e-5 single, 1e-12 double) is checked as well
+        rel_tol = 3e-5 if dtype == np.float32 else tol
+        assert np.linalg.norm(got[mask] - want[mask]) / np.linalg.norm(want[mask]) < rel_tol, uplo
+        assert np.linalg.norm(got[mask] - want[mask]) / n < {np.float64: 1e-12, np.float32: 1e-5, np.float16: 1e-2}[dtype], uplo
+    with pytest.raises(nla.NextLAError):
+        nla.lauum("X", nla.colmajor(np.eye(4, dtype=dtype)), 2)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lauum_reference_grid(nla, gpu, dtype):
+    """The reference's own lauum test (test/lauum.jl:1-29): n in {16, 32, 64, 128}, ib in {2, 4, 8}, both triangles, inputs
+    0.5 + rand (upper) / -0.5 + rand (lower) with a ZERO opposite triangle, criterion ||A - expected||_F / n < rtol
+    (1e-5 single, 1e-12 double, test/lapack_helpers.jl:14); and its error handling (:31-34)."""
+    import torch
+
+    rtol = 1e-12 if dtype == np.float64 else 1e-5
+    rng = np.random.RandomState(7)
+    for uplo, n, ib in itertools.product("UL", [16, 32, 64, 128], [2, 4, 8]):
+        A0 = (np.triu(0.5 + rng.rand(n, n)) if uplo == "U" else np.tril(-0.5 + rng.rand(n, n))).astype(dtype)
+        dA = nla.colmajor(A0)
+        nla.lauum(uplo, dA, ib)
+        torch.cuda.synchronize()
+        got = nla.to_numpy(dA).astype(np.float64)
+        A64 = A0.astype(np.float64)
+        expected = np.triu(A64 @ A64.T) if uplo == "U" else np.tril(A64.T @ A64)
+        tri = np.triu(got) if uplo == "U" else np.tril(got)
+        assert np.linalg.norm(tri - expected) / n < rtol, (uplo, n, ib)
+        other = np.tril(got, -1) if uplo == "U" else np.triu(got, 1)
+        assert not other.any()                                   # the zero triangle stays zero
+    with pytest.raises(nla.NextLAError):
+        nla.lauum("X", nla.colmajor(np.zeros((4, 4), dtype=dtype)), 2)
+    lib = nla.load_library()
+    assert lib.nla_lauum(gpu._h, b"U", 0, -1, None, 1, 2, None) == 2   # negative n (the reference: ArgumentError)

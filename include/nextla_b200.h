@@ -17,7 +17,10 @@ extern "C" {
 
 typedef struct nla_context *nla_handle_t;
 
-enum nla_dtype { NLA_F64 = 0, NLA_F32 = 1, NLA_F16 = 2 }; /* Float64 / Float32 / Float16 (src/rectrxm.jl:101: T<:AbstractFloat) */
+enum nla_dtype {
+  NLA_F64 = 0, NLA_F32 = 1, NLA_F16 = 2, /* Float64 / Float32 / Float16 (src/rectrxm.jl:101: T<:AbstractFloat) */
+  NLA_C64 = 3, NLA_C128 = 4              /* ComplexF32 / ComplexF64, interleaved (re, im): nla_rectrxm_complex only */
+};
 
 enum nla_status {
   NLA_OK = 0,
@@ -71,6 +74,14 @@ int nla_rectrxm(nla_handle_t handle, char side, char uplo, char trans, char func
  * (what the unit-lower solve of a recursive LU needs, src/lu.jl:277).  diag = 'N' is exactly nla_rectrxm. */
 int nla_trxm(nla_handle_t handle, char side, char uplo, char trans, char diag, char func, int dtype, int64_t n, int64_t m,
              double alpha, const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
+
+/* Complex element types: the same operation for ComplexF32 / ComplexF64 matrices (interleaved re/im, Julia layout),
+ * complex alpha, BLAS `diag` flag, and trans = 'C' (conjugate transpose) DISTINCT from 'T'.  The reference advertises complex support
+ * (README.md:20) and builds Adjoint(A) for 'C' (src/rectrxm.jl:57) but restricts the recursion to real types (:101), so a complex call
+ * fails there.  Runs the reference's recursion on planar copies of A and B in a library workspace (4 n^2 + 4 n m reals): every complex
+ * update is four real GEMM updates on the tensor-core kernels of the real path, diagonal blocks by complex substitution. */
+int nla_rectrxm_complex(nla_handle_t handle, char side, char uplo, char trans, char diag, char func, int dtype, int64_t n, int64_t m,
+                        double alpha_re, double alpha_im, const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
 
 /* Same operation with HOST buffers (pinned or pageable): stages A once and streams B through the device in
  * RHS slabs, overlapping copies with compute; synchronous (returns when B_host holds the result).

@@ -29,7 +29,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnextla_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "nextla_b200.h")
 
-NLA_F64, NLA_F32, NLA_F16 = 0, 1, 2
+NLA_F64, NLA_F32, NLA_F16, NLA_C64, NLA_C128 = 0, 1, 2, 3, 4
 _lib = None
 _handles = {}
 
@@ -56,6 +56,7 @@ def load_library():
         "nla_version": (I, []),
         "nla_probe_fp64_peak": (I, [H, c.POINTER(c.c_double)]),
         "nla_lauum": (I, [H, CH, I, L, P, L, L, P]),
+        "nla_rectrxm_complex": (I, [H, CH, CH, CH, CH, CH, I, L, L, D, D, P, L, P, L, P]),
         "nla_mg_create": (I, [c.POINTER(H), I, c.POINTER(c.c_int)]),
         "nla_mg_destroy": (I, [H]),
         "nla_mg_device_count": (I, [H]),
@@ -97,7 +98,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak", "nla_lauum",
+            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak", "nla_lauum", "nla_rectrxm_complex",
             "nla_mg_create", "nla_mg_destroy", "nla_mg_device_count", "nla_mg_handle", "nla_mg_stream", "nla_mg_last_nccl_error", "nla_mg_sync",
             "nla_mg_rectrxm", "nla_mg_rectrxm_host",
             "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
@@ -237,7 +238,7 @@ def _desc(t):
     ld = t.stride(1) if (cols > 1 and rows > 0) else max(1, rows)
     if ld < max(1, rows):
         raise NextLAError("invalid leading dimension")
-    code = {torch.float64: NLA_F64, torch.float32: NLA_F32, torch.float16: NLA_F16}.get(t.dtype)
+    code = {torch.float64: NLA_F64, torch.float32: NLA_F32, torch.float16: NLA_F16, torch.complex64: NLA_C64, torch.complex128: NLA_C128}.get(t.dtype)
     if code is None:
         raise NextLAError(f"unsupported dtype {t.dtype}")
     return t.data_ptr(), rows, cols, ld, code
@@ -270,6 +271,12 @@ def unified_rectrxm(side: str, uplo: str, transpose: str, alpha: float, func: st
     m = bc if side == "L" else br
     if (side == "L" and br != n) or (side == "R" and bc != n):
         raise NextLAError("dimension mismatch between A and B")
+    if dta in (NLA_C64, NLA_C128):   # complex element types: 'C' != 'T', complex alpha (nla_rectrxm_complex)
+        a = complex(alpha)
+        rc = load_library().nla_rectrxm_complex(h._h, _ch(side), _ch(uplo), _ch(transpose), b"N", _ch(func), dta, n, m, a.real, a.imag, pa, lda,
+                                                pb, ldb, _stream_ptr(stream, h.device))
+        _check(rc, h._h)
+        return B
     rc = load_library().nla_rectrxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
                                     _stream_ptr(stream, h.device))
     _check(rc, h._h)
@@ -377,6 +384,12 @@ def unified_trxm(side: str, uplo: str, transpose: str, diag: str, alpha: float, 
     m = bc if side == "L" else br
     if (side == "L" and br != n) or (side == "R" and bc != n):
         raise NextLAError("dimension mismatch between A and B")
+    if dta in (NLA_C64, NLA_C128):
+        a = complex(alpha)
+        rc = load_library().nla_rectrxm_complex(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(diag), _ch(func), dta, n, m, a.real, a.imag, pa, lda,
+                                                pb, ldb, _stream_ptr(stream, h.device))
+        _check(rc, h._h)
+        return B
     rc = load_library().nla_trxm(h._h, _ch(side), _ch(uplo), _ch(transpose), _ch(diag), _ch(func), dta, n, m, float(alpha), pa, lda, pb, ldb,
                                  _stream_ptr(stream, h.device))
     _check(rc, h._h)

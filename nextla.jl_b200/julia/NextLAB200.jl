@@ -6,7 +6,8 @@
 # No KernelAbstractions, no CPU fallback: a non-zero status raises.
 #
 # NOTE: Julia is not installed in the build/GPU images of this project, so this file is shipped UNEXECUTED; it is a
-# mechanical mirror of the ctypes binding in nextla.jl_b200/__init__.py, which is what the tests drive.
+# mechanical mirror of the ctypes binding in nextla.jl_b200/__init__.py, which is what the tests drive.  tests/test_abi.py checks, on
+# CPU, that every `ccall` in this file names a symbol the library exports and passes as many arguments as the C prototype declares.
 module NextLAB200
 
 using CUDA
@@ -29,18 +30,33 @@ function check(rc::Cint)
     error("nextla_b200: " * status_string(rc))
 end
 
-# one handle per (task-local) device
-const HANDLES = Dict{Int,Ptr{Cvoid}}()
+# One handle per (device, stream).  A handle owns device workspaces (block inverses, copies of B), so calls through one handle must be
+# ordered on one stream (include/nextla_b200.h); CUDA.jl gives every Julia task its own stream, hence the cache is keyed by the stream
+# handle as well: two tasks on one GPU never share workspaces.
+const HANDLES = Dict{Tuple{Int,UInt},Ptr{Cvoid}}()
 const HANDLES_LOCK = ReentrantLock()
 function handle()
     dev = CUDA.deviceid(CUDA.device())
+    key = (dev, UInt(Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)))
     lock(HANDLES_LOCK) do
-        get!(HANDLES, dev) do
+        get!(HANDLES, key) do
             h = Ref{Ptr{Cvoid}}(C_NULL)
             check(ccall((:nla_create, libnextla), Cint, (Ref{Ptr{Cvoid}}, Cint), h, dev))
             h[]
         end
     end
+end
+
+# Shape checks the C side cannot make (it only sees n, m and the leading dimensions): what the reference's generic kernels would
+# turn into a BoundsError becomes a DimensionMismatch here instead of an out-of-bounds device access.
+function check_shapes(side::Char, A, B)
+    n = size(A, 1)
+    size(A, 2) == n || throw(DimensionMismatch("A must be square, got $(size(A))"))
+    (side == 'L' || side == 'R') || throw(ArgumentError("side must be 'L' or 'R', got '$side'"))
+    nb = side == 'L' ? size(B, 1) : size(B, 2)
+    nb == n || throw(DimensionMismatch("B has $(nb) $(side == 'L' ? "rows" : "columns"), A is of order $n"))
+    (stride(A, 1) == 1 && stride(B, 1) == 1) || throw(ArgumentError("A and B must be column-major with unit row stride"))
+    return n, (side == 'L' ? size(B, 2) : size(B, 1))
 end
 
 """
@@ -51,9 +67,7 @@ task-local CUDA stream (the reference does not synchronise either, :75).
 """
 function NextLA.unified_rectrxm!(side::Char, uplo::Char, transpose::Char, alpha::Number, func::Char,
                                  A::StridedCuMatrix{T}, B::StridedCuMatrix{T}) where {T<:B200Float}
-    n = size(A, 1)
-    m = side == 'L' ? size(B, 2) : size(B, 1)
-    stride(A, 1) == 1 && stride(B, 1) == 1 || throw(ArgumentError("A and B must be column-major with unit row stride"))
+    n, m = check_shapes(side, A, B)
     GC.@preserve A B begin
         rc = ccall((:nla_rectrxm, libnextla), Cint,
                    (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
@@ -64,14 +78,29 @@ function NextLA.unified_rectrxm!(side::Char, uplo::Char, transpose::Char, alpha:
     return B
 end
 
+# Complex element types (SURVEY.md 8(f4)): the reference builds Adjoint(A) for transpose = 'C' (src/rectrxm.jl:57) but its recursion only
+# accepts real element types (:101); this method makes the advertised complex support (README.md:20) work, with 'C' distinct from 'T'.
+const B200Complex = Union{ComplexF32,ComplexF64}
+dtype_code(::Type{ComplexF32}) = Cint(3)
+dtype_code(::Type{ComplexF64}) = Cint(4)
+function NextLA.unified_rectrxm!(side::Char, uplo::Char, transpose::Char, alpha::Number, func::Char,
+                                 A::StridedCuMatrix{T}, B::StridedCuMatrix{T}) where {T<:B200Complex}
+    n, m = check_shapes(side, A, B)
+    a = ComplexF64(alpha)
+    GC.@preserve A B check(ccall((:nla_rectrxm_complex, libnextla), Cint,
+        (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
+        handle(), side, uplo, transpose, 'N', func, dtype_code(T), n, m, real(a), imag(a),
+        pointer(A), max(1, stride(A, 2)), pointer(B), max(1, stride(B, 2)), CUDA.stream().handle))
+    return B
+end
+
 # Leaf launchers (src/trsm.jl:128-150, src/trmm.jl:332-389) and GEMM updates (src/matmul.jl:69-81) on device matrices.
 for (fname, cfun, side, uplo) in ((:LeftLowerTRSM!, :nla_trsm_leaf, 'L', 'L'), (:LeftUpperTRSM!, :nla_trsm_leaf, 'L', 'U'),
                                   (:RightLowerTRSM!, :nla_trsm_leaf, 'R', 'L'), (:RightUpperTRSM!, :nla_trsm_leaf, 'R', 'U'),
                                   (:LeftLowerTRMM!, :nla_trmm_leaf, 'L', 'L'), (:LeftUpperTRMM!, :nla_trmm_leaf, 'L', 'U'),
                                   (:RightLowerTRMM!, :nla_trmm_leaf, 'R', 'L'), (:RightUpperTRMM!, :nla_trmm_leaf, 'R', 'U'))
     @eval function NextLA.$fname(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}; kwargs...) where {T<:B200Float}
-        n = size(A, 1)
-        m = $side == 'L' ? size(B, 2) : size(B, 1)
+        n, m = check_shapes($side, A, B)
         GC.@preserve A B check(ccall(($(QuoteNode(cfun)), libnextla), Cint,
             (Ptr{Cvoid}, Cchar, Cchar, Cint, Int64, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
             handle(), $side, $uplo, dtype_code(T), n, m, pointer(A), max(1, stride(A, 2)), pointer(B), max(1, stride(B, 2)), CUDA.stream().handle))
@@ -81,6 +110,7 @@ end
 
 function gemm_update!(C::StridedCuMatrix{T}, A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, sign::Integer) where {T<:B200Float}
     M, N, K = size(C, 1), size(C, 2), size(A, 2)
+    (size(A, 1) == M && size(B, 1) == K && size(B, 2) == N) || throw(DimensionMismatch("GEMM update: C is $(size(C)), A $(size(A)), B $(size(B))"))
     GC.@preserve A B C check(ccall((:nla_gemm_update, libnextla), Cint,
         (Ptr{Cvoid}, Cint, Cchar, Cchar, Int64, Int64, Int64, Cint, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
         handle(), dtype_code(T), 'N', 'N', M, N, K, Cint(sign), pointer(A), max(1, stride(A, 2)), pointer(B), max(1, stride(B, 2)),
@@ -96,8 +126,7 @@ NextLA.GEMM_SUB!(A::StridedCuMatrix{T}, B::StridedCuMatrix{T}, C::StridedCuMatri
 for (fname, func) in ((:trsm, 'S'), (:trmm, 'M'))
     @eval function NextLA.$fname(side::Char, uplo::Char, transa::Char, diag::Char, A::StridedCuMatrix{T}, B::StridedCuMatrix{T},
                                  alpha::Number = one(T)) where {T<:B200Float}
-        n = size(A, 1)
-        m = side == 'L' ? size(B, 2) : size(B, 1)
+        n, m = check_shapes(side, A, B)
         GC.@preserve A B check(ccall((:nla_trxm, libnextla), Cint,
             (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
             handle(), side, uplo, transa, diag, $func, dtype_code(T), n, m, Float64(alpha),
@@ -109,6 +138,7 @@ end
 # laswp(A, first, last, ipiv, incx) (src/lu.jl:470-530) on a device matrix; `ipiv` is a CuVector{Int64} (1-based, like the reference).
 # With trsm('L','L','N','U', ...) and GEMM_SUB! above this is every O(n^3) step of one level of getrf2! (src/lu.jl:274-280) on the device.
 function NextLA.laswp(A::StridedCuMatrix{T}, first::Integer, last::Integer, ipiv::CuVector{Int64}, incx::Integer) where {T<:B200Float}
+    (1 <= first && last <= min(size(A, 1), length(ipiv))) || last < first || throw(DimensionMismatch("laswp: rows $first:$last out of range"))
     GC.@preserve A ipiv check(ccall((:nla_laswp, libnextla), Cint,
         (Ptr{Cvoid}, Cint, Int64, Int64, CuPtr{Cvoid}, Int64, Int64, Int64, CuPtr{Int64}, Cint, Ptr{Cvoid}),
         handle(), dtype_code(T), size(A, 1), size(A, 2), pointer(A), max(1, stride(A, 2)), Int64(first), Int64(last), pointer(ipiv), Cint(incx),
@@ -125,8 +155,8 @@ for a panel right before the first launch that reads it.
 """
 function unified_rectrxm_gated!(side::Char, uplo::Char, transpose::Char, alpha::Number, func::Char, A::StridedCuMatrix{T},
                                 B::StridedCuMatrix{T}, panel_cols::Integer, events::Vector{CuEvent}) where {T<:B200Float}
-    n = size(A, 1)
-    m = side == 'L' ? size(B, 2) : size(B, 1)
+    n, m = check_shapes(side, A, B)
+    length(events) * panel_cols >= n || throw(DimensionMismatch("$(length(events)) panels of $panel_cols columns do not cover n = $n"))
     hs = Ptr{Cvoid}[Base.unsafe_convert(Ptr{Cvoid}, e.handle) for e in events]
     GC.@preserve A B events hs check(ccall((:nla_rectrxm_gated, libnextla), Cint,
         (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Int64, Cdouble, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Ptr{Ptr{Cvoid}}),
@@ -143,5 +173,60 @@ function panel_order(side::Char, uplo::Char, transpose::Char, func::Char, n::Int
     cnt < 0 && check(Cint(-cnt))
     return order   # 0-based panel indices in consumption order
 end
+
+"""
+    lauum!(uplo, n, A::StridedCuMatrix{T}, ib)
+
+Same signature as the reference (src/lauum.jl:52): A := U*U^H (uplo 'U') or L^H*L (uplo 'L') in the `uplo` triangle of the device matrix.
+Like the reference it throws ArgumentError for a bad `uplo` or a negative `n`.
+"""
+function NextLA.lauum!(uplo::Char, n::Integer, A::StridedCuMatrix{T}, ib::Integer) where {T<:B200Float}
+    uplo in ('U', 'L') || throw(ArgumentError("uplo must be 'U' or 'L', got '$uplo'"))
+    n >= 0 || throw(ArgumentError("n must be non-negative, got $n"))
+    (size(A, 1) >= n && size(A, 2) >= n) || throw(DimensionMismatch("A is $(size(A)), n = $n"))
+    n == 0 && return
+    GC.@preserve A check(ccall((:nla_lauum, libnextla), Cint, (Ptr{Cvoid}, Cchar, Cint, Int64, CuPtr{Cvoid}, Int64, Int64, Ptr{Cvoid}),
+                               handle(), uplo, dtype_code(T), n, pointer(A), max(1, stride(A, 2)), Int64(ib), CUDA.stream().handle))
+    return
+end
+
+# Workspace control (include/nextla_b200.h): by default the library grows its workspaces with the stream-ordered allocator, so calls stay
+# asynchronous; `reserve!` pre-sizes them, `set_workspace!` hands the library a CuVector{UInt8} arena (kept alive by the caller).
+workspace_bytes(side::Char, func::Char, ::Type{T}, n::Integer, m::Integer) where {T<:B200Float} =
+    ccall((:nla_workspace_bytes, libnextla), Int64, (Ptr{Cvoid}, Cchar, Cchar, Cint, Int64, Int64), handle(), side, func, dtype_code(T), n, m)
+reserve!(side::Char, func::Char, ::Type{T}, n::Integer, m::Integer) where {T<:B200Float} =
+    check(ccall((:nla_reserve, libnextla), Cint, (Ptr{Cvoid}, Cchar, Cchar, Cint, Int64, Int64), handle(), side, func, dtype_code(T), n, m))
+set_workspace!(buf::Union{Nothing,CuVector{UInt8}}) =
+    check(ccall((:nla_set_workspace, libnextla), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Int64), handle(),
+                buf === nothing ? CU_NULL : pointer(buf), buf === nothing ? 0 : length(buf)))
+
+# Single-process multi-GPU (nla_mg_*): the library owns the NCCL communicators, streams and replicas of A; B is sharded by the caller
+# (shard i on device i: columns of B for side 'L', rows for side 'R').  Asynchronous; `mg_sync` waits.
+mutable struct MultiGPU
+    ptr::Ptr{Cvoid}
+    function MultiGPU(devices::Vector{<:Integer} = collect(0:length(CUDA.devices())-1))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:nla_mg_create, libnextla), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), h, length(devices), Cint.(devices)))
+        mg = new(h[])
+        finalizer(m -> ccall((:nla_mg_destroy, libnextla), Cint, (Ptr{Cvoid},), m.ptr), mg)
+        return mg
+    end
+end
+function mg_rectrxm!(mg::MultiGPU, side::Char, uplo::Char, transpose::Char, alpha::Number, func::Char, root::Integer,
+                     A::StridedCuMatrix{T}, shards::Vector{<:StridedCuMatrix{T}}) where {T<:B200Float}
+    n = size(A, 1)
+    size(A, 2) == n || throw(DimensionMismatch("A must be square"))
+    for s in shards
+        (side == 'L' ? size(s, 1) : size(s, 2)) == n || throw(DimensionMismatch("shard of size $(size(s)) does not match n = $n"))
+    end
+    ptrs = CuPtr{Cvoid}[pointer(s) for s in shards]
+    ms = Int64[side == 'L' ? size(s, 2) : size(s, 1) for s in shards]
+    lds = Int64[max(1, stride(s, 2)) for s in shards]
+    GC.@preserve A shards check(ccall((:nla_mg_rectrxm, libnextla), Cint,
+        (Ptr{Cvoid}, Cchar, Cchar, Cchar, Cchar, Cint, Int64, Cdouble, Cint, CuPtr{Cvoid}, Int64, Ptr{CuPtr{Cvoid}}, Ptr{Int64}, Ptr{Int64}),
+        mg.ptr, side, uplo, transpose, func, dtype_code(T), n, Float64(alpha), root, pointer(A), max(1, stride(A, 2)), ptrs, ms, lds))
+    return shards
+end
+mg_sync(mg::MultiGPU) = check(ccall((:nla_mg_sync, libnextla), Cint, (Ptr{Cvoid},), mg.ptr))
 
 end # module

@@ -6,10 +6,12 @@ import numpy as np, torch
 import __graft_entry__ as ge
 from oracle import reference_port as rp
 nla = ge.load_package(); h = nla.default_handle(0)
+QUICK = "--quick" in sys.argv   # racecheck / synccheck are ~100x slower than memcheck: one size, the variants that differ in kernels
 worst = 0.0
 for dtype, tol in ((np.float16, 1e-2), (np.float32, 1e-5), (np.float64, 1e-13)):
-    for (n, m) in ((1300, 200), (2304, 136)):
-        for side, uplo, trans, func in itertools.product("LR", "LU", "NT", "SM"):
+    for (n, m) in (((1300, 200),) if QUICK else ((1300, 200), (2304, 136))):
+        for side, uplo, trans, func in ([("L", "L", "N", "S"), ("L", "U", "T", "S"), ("R", "L", "N", "S"), ("L", "L", "N", "M"), ("R", "U", "T", "M")] if QUICK
+                                        else itertools.product("LR", "LU", "NT", "SM")):
             A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=3, recipe="scaled")
             dA, dB = nla.colmajor(A), nla.colmajor(B0)
             nla.unified_trxm(side, uplo, trans, "N", 1.5, func, dA, dB); torch.cuda.synchronize()
@@ -30,4 +32,24 @@ ref = A.copy()
 for i, p in enumerate(piv.cpu().numpy()):
     ref[[i, p - 1]] = ref[[p - 1, i]]
 assert np.array_equal(nla.to_numpy(dA), ref)
+# lauum (triangle-masked GEMM epilogues) and the forced substitution fallback of the conditioning guard
+for dtype, tol in ((np.float64, 1e-13), (np.float32, 3e-5), (np.float16, 1e-2)):
+    n = 520
+    F = ((rng.rand(n, n) - 0.5) / np.sqrt(n) + np.eye(n)).astype(dtype)
+    for uplo in "LU":
+        T = np.tril(F) if uplo == "L" else np.triu(F)
+        dA = nla.colmajor(T); nla.lauum(uplo, dA, 256); torch.cuda.synchronize()
+        T64 = T.astype(np.float64); want = T64.T @ T64 if uplo == "L" else T64 @ T64.T
+        mask = np.tril(np.ones((n, n), bool)) if uplo == "L" else np.triu(np.ones((n, n), bool))
+        assert np.linalg.norm(nla.to_numpy(dA)[mask] - want[mask]) / np.linalg.norm(want[mask]) < tol
+h.set_option("inv_guard_kappa", 1)
+for dtype, tol in ((np.float16, 1e-2), (np.float32, 1e-5)):
+    for side, uplo in (("L", "L"), ("R", "U")):
+        A, B0 = rp.make_inputs(1304, 200, side, uplo, dtype, seed=4, recipe="scaled")   # 1304: a 16-byte pitch, i.e. the tensor-core path
+        dA, dB = nla.colmajor(A), nla.colmajor(B0)
+        nla.unified_rectrxm(side, uplo, "N", 1.0, "S", dA, dB); torch.cuda.synchronize()
+        fb = h.get_option("inv_fallbacks")
+        assert fb == 2, (dtype, side, uplo, fb)
+        assert rp.error_metric(side, uplo, "N", 1.0, "S", A, B0, nla.to_numpy(dB)) < tol
+h.set_option("inv_guard_kappa", 0)
 print("sanitize_small ok, worst err/tol", worst)

@@ -223,3 +223,30 @@ def test_host_pipeline_transfer_plan(nla, n, cutoff, slabs, resident):
             for c in range(c0 // TS, (c0 + cn - 1) // TS + 1):
                 writers[c] = oi
         assert [writers[c] for c in range(nt)] == last                                    # (4)
+
+
+def test_julia_binding_matches_the_c_prototypes(nla):
+    """The Julia side of the drop-in (nextla.jl_b200/julia/NextLAB200.jl) cannot be executed here (no Julia in the image), so it is
+    checked statically: every `ccall` names a symbol that include/nextla_b200.h declares and the library exports, and its argument-type
+    tuple has exactly as many entries as the C prototype has parameters; every wrapper that takes matrices validates their shapes
+    (a mismatched call must raise DimensionMismatch instead of reaching the device)."""
+    lib = nla.load_library()
+    header = open(os.path.join(ROOT, "include", "nextla_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(nla_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    jl = open(os.path.join(ROOT, "nextla.jl_b200", "julia", "NextLAB200.jl")).read()
+    calls = re.findall(r"ccall\(\((?::(\w+)|\$\(QuoteNode\(cfun\)\)),\s*libnextla\),\s*\w+,\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 15
+    for name, types in calls:
+        names = [name] if name else ["nla_trsm_leaf", "nla_trmm_leaf"]
+        ntypes = len([t for t in types.split(",") if t.strip()])
+        for nm in names:
+            assert nm in protos, f"{nm} is not declared in the header"
+            assert hasattr(lib, nm), f"{nm} is not exported"
+            assert ntypes == protos[nm], f"ccall of {nm} passes {ntypes} argument types, the C prototype has {protos[nm]}"
+    # shape validation in every matrix-taking wrapper; handles keyed by (device, stream)
+    assert jl.count("check_shapes(") >= 5 and "DimensionMismatch" in jl
+    assert "Dict{Tuple{Int,UInt},Ptr{Cvoid}}" in jl and "CUDA.stream().handle" in jl

@@ -502,6 +502,31 @@ def main():
                    "is their NCCL root (ncclBroadcast per panel, consumption order) + nla_rectrxm_hostb_gated (B streamed in chunks, launches gated on the panels of A)")
             extra_e2e = {"numa": sharded.numa_report(local)}
 
+        # the box's own ceiling for this traffic pattern: every rank at once copies its 2 GiB of B host -> device and 2 GiB device -> host
+        # (pinned buffers, two streams, nothing else running); e2e can never beat max(compute, bytes / this)
+        link = None
+        try:
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            best = 1e30
+            for _ in range(2):
+                sync_all()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_up):
+                    X.t().copy_(hostB, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    hostX.copy_(B0.t(), non_blocking=True)
+                torch.cuda.synchronize()
+                dtw = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(dtw, op=dist.ReduceOp.MAX)
+                best = min(best, dtw.item())
+            nb = n * m * es
+            link = {"concurrent_h2d_plus_d2h_seconds": best, "per_rank_gbs_each_direction": nb / best * 1e-9,
+                    "aggregate_gbs_both_directions": 2 * nb * world / best * 1e-9,
+                    "what": f"all {world} ranks at once: {nb / 2**30:.0f} GiB pinned host -> device and {nb / 2**30:.0f} GiB device -> pinned host per rank on two streams"}
+        except Exception as e:  # noqa: BLE001
+            link = {"error": repr(e)}
+
         e2e_step()
         sync_all()
         tt = 0.0
@@ -525,7 +550,13 @@ def main():
                "h2d_bytes_per_step": a_bytes + n * m * world * es, "d2h_bytes_per_step": n * m * world * es, "steps": e2e_steps,
                "ms_per_step": sec * 1e3, "api": api,
                "h2d_gbs_per_rank": (a_bytes / world + n * m * es) / sec * 1e-9, "d2h_gbs_per_rank": n * m * es / sec * 1e-9,
-               "host_buffers": "pinned (cudaHostAlloc / cudaHostRegister)"}
+               "host_buffers": "pinned (cudaHostAlloc / cudaHostRegister)", "host_link_ceiling": link}
+        if link and "concurrent_h2d_plus_d2h_seconds" in link:
+            # lower bound of any end-to-end step on this box: the B traffic alone at the measured ceiling, or the device-resident step
+            e2e["floor_ms_per_step"] = max(link["concurrent_h2d_plus_d2h_seconds"] * 1e3, total_ms / args.steps)
+            e2e["limiter"] = ("host link: the step moves %.1f GB through one host at %.0f GB/s aggregate (measured ceiling of this box for this pattern)"
+                              % ((e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) * 1e-9, link["aggregate_gbs_both_directions"])
+                              if link["concurrent_h2d_plus_d2h_seconds"] * 1e3 > total_ms / args.steps else "compute: transfers hide behind the solve")
         e2e.update(extra_e2e)
         # check the e2e result too
         Xh = hostX.to(dev).t()

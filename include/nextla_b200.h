@@ -175,6 +175,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
  *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 2048, 0 = off)
+ *   "slab_w"      right-hand-side vectors per CTA of the fused slab kernel: 0 = automatic (128; 64 when the call has at most 64 x #SM vectors,
+ *                 so that few right-hand sides still spread over the machine), 64, 128
  *   "streams"     number of RHS slabs run on concurrent streams (0 = automatic: one per 4096 vectors, at most 4)
  *   "tc_bn"       N tile of the Float32/Float16 tcgen05 GEMM: 0 = automatic (256, or 128 when the 256-wide grid would not fill the SMs), 128, 256
  *   "tc_cg"       CTA pairs (tcgen05 cta_group::2, 256 x 256 tile per pair) for the large updates: 0 = automatic, 1 = never, 2 = whenever M > 128

@@ -89,6 +89,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 1) tmem_alloc2(smem_u32(&tmem_slot), TMEM_COLS);
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapB); }
   tc_fence_before();
+  __syncthreads();      // CTA-level ordering of the TMEM address written by tcgen05.alloc (the cluster barrier below covers it too, but
+                        // compute-sanitizer racecheck only models CTA barriers for shared-memory hazards)
   cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated in both SMs
   tc_fence_after();
   asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -49,6 +49,7 @@ struct nla_context {
   int64_t tc_chunk_k;   // see GemmTcParams::chunk_k
   int sm_count;
   int64_t macro;        // order of the diagonal blocks handled by the fused slab kernel (0 = disabled)
+  int64_t slab_w;       // vectors per CTA of the fused slab kernel: 0 = automatic, 64 (two CTAs per SM) or 128
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
@@ -265,11 +266,11 @@ static int launch_gemm_simt(nla_context* ctx, int64_t M, int64_t N, int64_t K, c
 
 // TMA descriptor for a column-major FP64 matrix (rows x cols, leading dimension ld) viewed as
 // {8 rows, cols, rows/8}: MN-major operands take boxes {8,16,16}, K-major operands {8,128,2}.
-static bool encode_map(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj) {
+static bool encode_map(nla_context* ctx, CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int maj, unsigned kbox = 128) {
   if (!ctx->encode) return false;
   cuuint64_t dims[3] = {8, (cuuint64_t)cols, (cuuint64_t)(rows / 8)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 8, 64};
-  cuuint32_t box[3] = {8, maj == MAJ_MN ? 16u : 128u, maj == MAJ_MN ? 16u : 2u};
+  cuuint32_t box[3] = {8, maj == MAJ_MN ? 16u : kbox, maj == MAJ_MN ? 16u : 2u};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(ptr), dims, strides, box, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -291,14 +292,25 @@ static int launch_gemm_f64_tma(nla_context* ctx, const CUtensorMap& mA, const CU
   return NLA_OK;
 }
 
-template <int AMAJ, bool LOWER, bool SOLVE>
-static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV, const SlabParams& sp, cudaStream_t st) {
-  { int arc = ensure_smem_attr(ctx, slab_f64_kernel<AMAJ, LOWER, SOLVE>, SL_SMEM_BYTES); if (arc != NLA_OK) return arc; }
-  const unsigned grid = (unsigned)((sp.v_count + SL_W - 1) / SL_W);
-  slab_f64_kernel<AMAJ, LOWER, SOLVE><<<grid, SL_THREADS, SL_SMEM_BYTES, st>>>(mT, mV, sp);
+template <int AMAJ, bool LOWER, bool SOLVE, int W>
+static int launch_slab_w(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV, const SlabParams& sp, cudaStream_t st) {
+  { int arc = ensure_smem_attr(ctx, slab_f64_kernel<AMAJ, LOWER, SOLVE, W>, SlabCfg<W>::SMEM_BYTES); if (arc != NLA_OK) return arc; }
+  const unsigned grid = (unsigned)((sp.v_count + W - 1) / W);
+  slab_f64_kernel<AMAJ, LOWER, SOLVE, W><<<grid, SlabCfg<W>::THREADS, SlabCfg<W>::SMEM_BYTES, st>>>(mT, mV, sp);
   ctx->launches++;
   NLA_CUDA(ctx, cudaGetLastError());
   return NLA_OK;
+}
+
+// option "slab_w": vectors per CTA.  128 = the throughput shape (8 consumer warps, two per SM sub-partition).  64 halves the CTA so
+// that a call with few right-hand sides still spreads over the machine: with m <= 64 x #SM vectors in total, 64-wide CTAs put one CTA
+// on twice as many SMs (C5: 8192 vectors -> 128 instead of 64 of the 148 SMs).  (Two 64-wide CTAs per SM on a large m were measured
+// equal to one 128-wide CTA: they run in lockstep, their diagonal phases coincide.)  mV128 / mV64: TMA maps of V with the matching box.
+template <int AMAJ, bool LOWER, bool SOLVE>
+static int launch_slab_variant(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV128, const CUtensorMap& mV64, const SlabParams& sp, cudaStream_t st) {
+  const int64_t w = ctx->slab_w > 0 ? ctx->slab_w : (sp.m_total <= 64ll * ctx->sm_count ? 64 : 128);
+  if (w == 64) return launch_slab_w<AMAJ, LOWER, SOLVE, 64>(ctx, mT, mV64, sp, st);
+  return launch_slab_w<AMAJ, LOWER, SOLVE, 128>(ctx, mT, mV128, sp, st);
 }
 
 // ---- Float32 / Float16 tensor-core path (gemm_tc.cuh, diag_prep.cuh) ------------------------------------------------------
@@ -489,6 +501,7 @@ struct TmaMaps {
   bool fused;        // diagonal blocks go to the fused slab kernel (left side, FP64, TMA-eligible)
   CUtensorMap mapT;  // triangular matrix A in the majorness its GEMM role needs
   CUtensorMap mapV;  // B in the majorness its GEMM role needs
+  CUtensorMap mapV64;   // the same matrix with a 64-vector box (fused slab kernel, two CTAs per SM)
   // Float32 / Float16 tensor-core path: mapT / mapV as above (2-D, SWIZZLE_128B), mapW = prepared diagonal blocks (K-major)
   bool tc;
   bool prep_per_leaf;   // host-buffer pipeline: a block is prepared right before its leaf (its tile of A has just arrived)
@@ -642,16 +655,17 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
   sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
   sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = o.pre; sp.post = o.post; sp.unit = P.unit;
   sp.dbg = (unsigned long long*)ctx->tc_dbg;
+  sp.m_total = P.m;
   const int v = (P.teff_trans ? 4 : 0) | (P.lower ? 2 : 0) | (P.solve ? 1 : 0);
   switch (v) {
-    case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 1: return launch_slab_variant<MAJ_MN, false, true>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 2: return launch_slab_variant<MAJ_MN, true, false>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 3: return launch_slab_variant<MAJ_MN, true, true>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 4: return launch_slab_variant<MAJ_K, false, false>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 5: return launch_slab_variant<MAJ_K, false, true>(ctx, maps.mapT, maps.mapV, sp, st);
-    case 6: return launch_slab_variant<MAJ_K, true, false>(ctx, maps.mapT, maps.mapV, sp, st);
-    default: return launch_slab_variant<MAJ_K, true, true>(ctx, maps.mapT, maps.mapV, sp, st);
+    case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 1: return launch_slab_variant<MAJ_MN, false, true>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 2: return launch_slab_variant<MAJ_MN, true, false>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 3: return launch_slab_variant<MAJ_MN, true, true>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 4: return launch_slab_variant<MAJ_K, false, false>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 5: return launch_slab_variant<MAJ_K, false, true>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    case 6: return launch_slab_variant<MAJ_K, true, false>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
+    default: return launch_slab_variant<MAJ_K, true, true>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
   }
 }
 
@@ -926,7 +940,8 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_
       for (const Op& o : ops)
         if (o.kind == Op::LEAF && ((o.off % 8) || ((o.sz % SL_BM) && (o.off + o.sz != P.n)))) ok = false;
       if (ok) maps.fused = maps.ok = encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) &&
-                                     encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV);
+                                     encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV) &&
+                                     encode_map(ctx, &maps.mapV64, P.B, brows, bcols, P.ldb, majV, 64);
       if (!maps.ok) ops.clear();
     }
     if (!maps.ok) {
@@ -1270,7 +1285,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
+  ctx->slab_w = 0; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1315,6 +1330,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
+  if (!strcmp(key, "slab_w")) { if (value != 0 && value != 64 && value != 128) return NLA_ERR_INVALID_DIM; h->slab_w = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
   if (!strcmp(key, "tc_cg")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_cg = value; return NLA_OK; }
   if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
@@ -1346,6 +1362,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "streams")) return h->nstreams;
   if (!strcmp(key, "profile")) return h->profile;
   if (!strcmp(key, "macro")) return h->macro;
+  if (!strcmp(key, "slab_w")) return h->slab_w;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
   if (!strcmp(key, "tc_cg")) return h->tc_cg;
   if (!strcmp(key, "tf32_raw_hi")) return h->tf32_raw_hi;

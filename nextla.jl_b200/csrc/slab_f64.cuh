@@ -21,21 +21,34 @@
 
 namespace nla {
 
-constexpr int SL_BM = 128, SL_W = 128, SL_BK = 16, SL_STAGES = 4;
-constexpr int SL_TILE_BYTES = SL_BM * SL_BK * 8;
-constexpr int SL_STAGE_BYTES = 2 * SL_TILE_BYTES;
-constexpr int SL_CONSUMER_WARPS = 8;
-constexpr int SL_THREADS = (SL_CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (1 active warp)
+constexpr int SL_BM = 128, SL_BK = 16;
+constexpr int SL_TILE_BYTES = SL_BM * SL_BK * 8;                        // one 128 x 16 tile of Teff
 constexpr int SL_SCR_PITCH = 9;                                        // doubles per column of a warp's 8 x 16 exchange tile (8 rows + 1 pad)
-constexpr int SL_SCRATCH_BYTES = SL_CONSUMER_WARPS * 16 * SL_SCR_PITCH * 8;
 constexpr int SL_LP_DOUBLES = 16 * 64 + 128;                            // per block row: 16 scaled 8 x 8 micro-blocks + 128 reciprocal diagonals
 constexpr int SL_LP_BYTES = 2 * SL_LP_DOUBLES * 8;                      // double-buffered by block-row parity
-constexpr int SL_SMEM_BYTES = SL_STAGES * SL_STAGE_BYTES + SL_SCRATCH_BYTES + SL_LP_BYTES + 1024;
+
+// Machine mapping: a CTA owns W right-hand-side vectors, one consumer warp per 16 of them, plus a warpgroup that holds the TMA producer
+// warp and the helper warp and hands most of its registers to the consumers (setmaxnreg).
+//   W = 128: one CTA per SM (8 consumer warps, 4-stage ring).
+//   W = 64 : TWO CTAs per SM (4 consumer warps each, 3-stage rings).  The two CTAs of an SM are independent (different vectors) and drift
+//            apart, so one runs its latency-bound diagonal phase / write-back while the other keeps the FP64 tensor pipe busy.
+template <int W> struct SlabCfg {
+  static constexpr int CW = W / 16;
+  static constexpr int THREADS = (CW + 4) * 32;
+  static constexpr int CONSUMER_REGS = W == 128 ? 232 : 216;   // 12 warps x 168 -> 8 x 232 + 4 x 40;   2 CTAs x (8 warps x 128 -> 4 x 216 + 4 x 40)
+  static constexpr int STAGES = W == 128 ? 4 : 3;
+  static constexpr int B_BYTES = W * SL_BK * 8;
+  static constexpr int STAGE_BYTES = SL_TILE_BYTES + B_BYTES;
+  static constexpr int SCRATCH_BYTES = CW * 16 * SL_SCR_PITCH * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SCRATCH_BYTES + SL_LP_BYTES + 1024;
+  static constexpr int MIN_CTAS = W == 128 ? 1 : 2;
+};
 
 struct SlabParams {
   int T;                  // order of the diagonal block
   int off;                // its origin (row == column) in Teff coordinates
   int v_base, v_count;    // vectors (columns of B) handled by this launch
+  long long m_total;      // vectors of the whole call (host side: picks the CTA width)
   const double* A;        // Teff(r,c) = A[r*t_rs + c*t_cs]
   long long t_rs, t_cs;
   double* B;              // column-major, vectors are columns
@@ -47,9 +60,11 @@ struct SlabParams {
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int AMAJ, bool LOWER, bool SOLVE>
-__global__ void __launch_bounds__(SL_THREADS, 1)
+template <int AMAJ, bool LOWER, bool SOLVE, int W>
+__global__ void __launch_bounds__(SlabCfg<W>::THREADS, SlabCfg<W>::MIN_CTAS)
 slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapV, const SlabParams p) {
+  using Cfg = SlabCfg<W>;
+  constexpr int SL_W = W, SL_STAGES = Cfg::STAGES, SL_STAGE_BYTES = Cfg::STAGE_BYTES, SL_CONSUMER_WARPS = Cfg::CW, SL_SCRATCH_BYTES = Cfg::SCRATCH_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[SL_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[SL_STAGES];
@@ -85,7 +100,7 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
   auto ktiles = [&](int j) { return (min(SL_BM, p.T - j * SL_BM) + SL_BK - 1) / SL_BK; };
 
   if (warp >= SL_CONSUMER_WARPS) {
-    // ===== TMA producer warpgroup: hands its registers to the consumers, one lane of one warp issues the copies =====
+    // ===== producer warpgroup: hands its registers to the consumers; warp 0 of it issues the TMA copies (one lane), warp 1 is the helper =====
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == SL_CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&mapT);
@@ -175,7 +190,7 @@ slab_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant_
   }
 
   // ===== consumers: warp w owns vectors [16w, 16w+16) of the slab, all 128 rows =====
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::CONSUMER_REGS));
   const uint32_t g = lane >> 2, q = lane & 3;
   uint32_t aoff[4], boff[4];
   uint32_t kloc[4];  // k index (0..15) inside the tile handled by this lane at each step

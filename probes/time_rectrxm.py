@@ -8,8 +8,11 @@ ap.add_argument("--n", type=int, default=16384); ap.add_argument("--m", type=int
 ap.add_argument("--side", default="L"); ap.add_argument("--uplo", default="L"); ap.add_argument("--trans", default="N"); ap.add_argument("--func", default="S")
 ap.add_argument("--dtype", default="float64"); ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--streams", default="1"); ap.add_argument("--leaf", default="128"); ap.add_argument("--macro", default="1024")
+ap.add_argument("--opt", default="", help="k=v,k=v handle options")
 a = ap.parse_args()
 nla = ge.load_package(); h = nla.default_handle(0)
+for kv in filter(None, a.opt.split(",")):
+    k, v = kv.split("="); h.set_option(k, int(v))
 dt = getattr(torch, a.dtype); n, m = a.n, a.m
 g = torch.Generator(device="cuda").manual_seed(1)
 A = (2 * torch.rand(n, n, dtype=torch.float32, device="cuda", generator=g) - 1).to(dt) / n ** 0.5
@@ -31,4 +34,4 @@ for st in [int(s) for s in a.streams.split(",")]:
             if r > 0: ts.append(e0.elapsed_time(e1))
         ms = min(ts); fl = n * n * m
         print(json.dumps({"n": n, "m": m, "case": a.side + a.uplo + a.trans + a.func, "dtype": a.dtype, "streams": st, "leaf": leaf, "macro": macro, "ms_min": round(ms, 3),
-                          "ms_all": [round(t, 2) for t in ts], "tflops": round(fl / ms * 1e-9, 2), "launches": h.launch_count()}), flush=True)
+                          "ms_all": [round(t, 2) for t in ts], "tflops": round(fl / ms * 1e-9, 2), "launches": h.launch_count(), "opt": a.opt}), flush=True)

@@ -174,9 +174,11 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
 /* Tunables (the reference hard-codes its thresholds, src/rectrxm.jl:52,63).  Keys:
  *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
- *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 2048, 0 = off)
- *   "slab_w"      right-hand-side vectors per CTA of the fused slab kernel: 0 = automatic (128; 64 when the call has at most 64 x #SM vectors,
- *                 so that few right-hand sides still spread over the machine), 64, 128
+ *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 4096, 0 = off)
+ *   "slab_kind"   fused FP64 slab kernel: 0 (default) = row-split (the 8 consumer warps share the 128 rows of a block row; CTA width 112 or
+ *                 56 vectors, whichever fills the 148 SMs best for the call's number of right-hand sides), 1 = column-split (128 / 64 vectors)
+ *   "slab_w"      right-hand-side vectors per CTA of the fused slab kernel: 0 = automatic; 112 / 56 force a width of the row-split kernel,
+ *                 128 / 64 select the column-split kernel with that width
  *   "streams"     number of RHS slabs run on concurrent streams (0 = automatic: one per 4096 vectors, at most 4)
  *   "tc_bn"       N tile of the Float32/Float16 tcgen05 GEMM: 0 = automatic (256, or 128 when the 256-wide grid would not fill the SMs), 128, 256
  *   "tc_cg"       CTA pairs (tcgen05 cta_group::2, 256 x 256 tile per pair) for the large updates: 0 = automatic, 1 = never, 2 = whenever M > 128
@@ -214,7 +216,7 @@ int64_t nla_get_option(nla_handle_t handle, const char *key);
 /* Host-only introspection of the schedule that replaces the recursive splitter (src/rectrxm.jl:101-198): writes up to
  * max_ops records of 6 int64 {kind (0 = leaf, 1 = GEMM update), c0, cn, k0, kn, carries_alpha} in launch order, in the
  * normalised coordinates of DESIGN.md (leaf: diagonal block [c0, c0+cn); update: V[c0:c0+cn] +-= Teff[c,k] V[k0:k0+kn]).
- * `leaf` = recursion cutoff: <= 0 -> 128; up to 4096 (2048 = the fused FP64 slab schedule, 1024 = the block-inverse Float32/Float16 one).
+ * `leaf` = recursion cutoff: <= 0 -> 128; up to 4096 (4096 = the fused FP64 slab schedule, 1024 = the block-inverse Float32/Float16 one).
  * Returns the number of ops (may exceed max_ops) or a negative nla_status.  Needs no GPU. */
 int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t leaf, int64_t *ops, int64_t max_ops);
 

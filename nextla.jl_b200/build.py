@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnextla_b200.so")
 SOURCES = ["nla_api.cu"]
-HEADERS = ["common.cuh", "probe.cuh", "complex.cuh", "nla_mg.cuh", "tri_guard.cuh", "tri_inv.cuh", "laswp.cuh", "gemm_f64.cuh", "gemm_simt.cuh", "leaf.cuh", "slab_f64.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc3.cuh", "gemm_tc4.cuh", "diag_prep.cuh"]
+HEADERS = ["common.cuh", "probe.cuh", "complex.cuh", "nla_mg.cuh", "tri_guard.cuh", "tri_inv.cuh", "laswp.cuh", "gemm_f64.cuh", "gemm_simt.cuh", "leaf.cuh", "slab_f64.cuh", "slab2_f64.cuh", "gemm_tc.cuh", "gemm_tc2.cuh", "gemm_tc3.cuh", "gemm_tc4.cuh", "diag_prep.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 

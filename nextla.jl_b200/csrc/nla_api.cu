@@ -15,6 +15,7 @@
 #include "gemm_simt.cuh"
 #include "leaf.cuh"
 #include "slab_f64.cuh"
+#include "slab2_f64.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
@@ -49,7 +50,9 @@ struct nla_context {
   int64_t tc_chunk_k;   // see GemmTcParams::chunk_k
   int sm_count;
   int64_t macro;        // order of the diagonal blocks handled by the fused slab kernel (0 = disabled)
-  int64_t slab_w;       // vectors per CTA of the fused slab kernel: 0 = automatic, 64 (two CTAs per SM) or 128
+  int64_t slab_w;       // vectors per CTA of the fused slab kernel: 0 = automatic; 56 / 112 row-split kernel, 64 / 128 column-split kernel
+  int64_t slab_kind;    // 0 = row-split kernel (slab2_f64.cuh), 1 = column-split kernel (slab_f64.cuh)
+  int64_t host_macro, host_macro_mid;   // host pipeline: fused-slab block order at the ends / in the middle of the diagonal
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
@@ -164,6 +167,9 @@ struct Problem {
   const void* A; int64_t lda;
   void* B; int64_t ldb;
   int64_t es, vs;    // element / vector strides inside B
+  // optional finer recursion cutoff for the blocks that touch the first / last `edge_span` unknowns (host pipeline: small blocks where
+  // the transfers cannot hide -- the first leaf waits for its chunk of B, the last download waits for the last leaf -- large ones between)
+  int64_t edge_leaf = 0, edge_span = 0;
 };
 
 struct Op {
@@ -178,7 +184,8 @@ struct Op {
 // (the reference scales all of B up front, :64; here alpha is folded into the first kernel that touches a
 // block).  `final`: for 'M' no later update touches the block, so alpha (:72) is folded into this one.
 static void build_schedule(const Problem& P, int64_t leaf, int64_t off, int64_t n, bool scaled, bool final, std::vector<Op>& ops) {
-  if (n <= leaf) {
+  const bool at_edge = P.edge_leaf > 0 && (off < P.edge_span || off + n > P.n - P.edge_span);
+  if (n <= (at_edge ? std::min(leaf, P.edge_leaf) : leaf)) {
     Op o{};
     o.kind = Op::LEAF; o.off = off; o.sz = n;
     o.pre = (P.solve && !scaled) ? P.alpha : 1.0;
@@ -501,7 +508,8 @@ struct TmaMaps {
   bool fused;        // diagonal blocks go to the fused slab kernel (left side, FP64, TMA-eligible)
   CUtensorMap mapT;  // triangular matrix A in the majorness its GEMM role needs
   CUtensorMap mapV;  // B in the majorness its GEMM role needs
-  CUtensorMap mapV64;   // the same matrix with a 64-vector box (fused slab kernel, two CTAs per SM)
+  CUtensorMap mapV64;   // the same matrix with a 64-vector box (column-split slab kernel with 64-wide CTAs)
+  CUtensorMap mapV112, mapV56;   // ... and with 112- / 56-vector boxes (row-split slab kernel)
   // Float32 / Float16 tensor-core path: mapT / mapV as above (2-D, SWIZZLE_128B), mapW = prepared diagonal blocks (K-major)
   bool tc;
   bool prep_per_leaf;   // host-buffer pipeline: a block is prepared right before its leaf (its tile of A has just arrived)
@@ -647,6 +655,38 @@ static int launch_update(nla_context* ctx, const Problem& P, const TmaMaps& maps
                              sgn, o.post, st);
 }
 
+// Row-split fused macro-leaf (slab2_f64.cuh): CTA width 8 * NB vectors
+template <int AMAJ, bool LOWER, bool SOLVE, int NB>
+static int launch_slab2_nb(nla_context* ctx, const CUtensorMap& mT, const CUtensorMap& mV, const SlabParams& sp, cudaStream_t st) {
+  using Cfg = Slab2Cfg<NB>;
+  { int arc = ensure_smem_attr(ctx, slab2_f64_kernel<AMAJ, LOWER, SOLVE, NB>, Cfg::SMEM_BYTES); if (arc != NLA_OK) return arc; }
+  const unsigned grid = (unsigned)((sp.v_count + Cfg::W - 1) / Cfg::W);
+  slab2_f64_kernel<AMAJ, LOWER, SOLVE, NB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mT, mV, sp);
+  ctx->launches++;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+// CTA width of the row-split kernel: the one that finishes the whole call's right-hand sides in the fewest "waves x width" (all RHS
+// slabs of the call run concurrently on their streams): 16384 vectors -> 112 (147 CTAs), 8192 -> 56 (147 CTAs); ties go to the wider CTA.
+static int pick_slab2_width(const nla_context* ctx, const SlabParams& sp) {
+  if (ctx->slab_w == 56 || ctx->slab_w == 112) return (int)ctx->slab_w;
+  const int64_t nslabs = std::max<int64_t>(1, (sp.m_total + sp.v_count - 1) / std::max(1, sp.v_count));
+  int best_w = 112; int64_t best = -1;
+  for (int w : {112, 56}) {
+    const int64_t ctas = nslabs * ((sp.v_count + w - 1) / w);
+    const int64_t cost = ((ctas + ctx->sm_count - 1) / ctx->sm_count) * w;
+    if (best < 0 || cost < best) { best = cost; best_w = w; }
+  }
+  return best_w;
+}
+
+template <int AMAJ, bool LOWER, bool SOLVE>
+static int launch_slab2_variant(nla_context* ctx, const TmaMaps& maps, const SlabParams& sp, cudaStream_t st) {
+  if (pick_slab2_width(ctx, sp) == 56) return launch_slab2_nb<AMAJ, LOWER, SOLVE, 7>(ctx, maps.mapT, maps.mapV56, sp, st);
+  return launch_slab2_nb<AMAJ, LOWER, SOLVE, 14>(ctx, maps.mapT, maps.mapV112, sp, st);
+}
+
 // Fused macro-leaf for a LEAF op (left side, FP64): see slab_f64.cuh
 static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, const Op& o, int64_t v0, int64_t nv, cudaStream_t st) {
   SlabParams sp{};
@@ -657,6 +697,18 @@ static int launch_slab(nla_context* ctx, const Problem& P, const TmaMaps& maps, 
   sp.dbg = (unsigned long long*)ctx->tc_dbg;
   sp.m_total = P.m;
   const int v = (P.teff_trans ? 4 : 0) | (P.lower ? 2 : 0) | (P.solve ? 1 : 0);
+  if (ctx->slab_kind != 1 && ctx->slab_w != 64 && ctx->slab_w != 128) {   // default: the row-split kernel (fills the machine for any m)
+    switch (v) {
+      case 0: return launch_slab2_variant<MAJ_MN, false, false>(ctx, maps, sp, st);
+      case 1: return launch_slab2_variant<MAJ_MN, false, true>(ctx, maps, sp, st);
+      case 2: return launch_slab2_variant<MAJ_MN, true, false>(ctx, maps, sp, st);
+      case 3: return launch_slab2_variant<MAJ_MN, true, true>(ctx, maps, sp, st);
+      case 4: return launch_slab2_variant<MAJ_K, false, false>(ctx, maps, sp, st);
+      case 5: return launch_slab2_variant<MAJ_K, false, true>(ctx, maps, sp, st);
+      case 6: return launch_slab2_variant<MAJ_K, true, false>(ctx, maps, sp, st);
+      default: return launch_slab2_variant<MAJ_K, true, true>(ctx, maps, sp, st);
+    }
+  }
   switch (v) {
     case 0: return launch_slab_variant<MAJ_MN, false, false>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
     case 1: return launch_slab_variant<MAJ_MN, false, true>(ctx, maps.mapT, maps.mapV, maps.mapV64, sp, st);
@@ -941,7 +993,9 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_
         if (o.kind == Op::LEAF && ((o.off % 8) || ((o.sz % SL_BM) && (o.off + o.sz != P.n)))) ok = false;
       if (ok) maps.fused = maps.ok = encode_map(ctx, &maps.mapT, P.A, P.n, P.n, P.lda, majT) &&
                                      encode_map(ctx, &maps.mapV, P.B, brows, bcols, P.ldb, majV) &&
-                                     encode_map(ctx, &maps.mapV64, P.B, brows, bcols, P.ldb, majV, 64);
+                                     encode_map(ctx, &maps.mapV64, P.B, brows, bcols, P.ldb, majV, 64) &&
+                                     encode_map(ctx, &maps.mapV112, P.B, brows, bcols, P.ldb, majV, 112) &&
+                                     encode_map(ctx, &maps.mapV56, P.B, brows, bcols, P.ldb, majV, 56);
       if (!maps.ok) ops.clear();
     }
     if (!maps.ok) {
@@ -1274,7 +1328,7 @@ int nla_create(nla_handle_t* handle, int device) {
   nla_context* ctx = new (std::nothrow) nla_context();
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
-  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 2048;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 4096;
   ctx->tc_bn = 0; ctx->tc_cg = 0; ctx->tf32_raw_hi = 1; ctx->tc_chunk_k = TcCfg<float>::CHUNK_K; ctx->sm_count = 148;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
@@ -1285,7 +1339,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->slab_w = 0; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
+  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1330,7 +1384,10 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
   if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
-  if (!strcmp(key, "slab_w")) { if (value != 0 && value != 64 && value != 128) return NLA_ERR_INVALID_DIM; h->slab_w = value; return NLA_OK; }
+  if (!strcmp(key, "slab_w")) { if (value != 0 && value != 56 && value != 64 && value != 112 && value != 128) return NLA_ERR_INVALID_DIM; h->slab_w = value; return NLA_OK; }
+  if (!strcmp(key, "slab_kind")) { if (value < 0 || value > 1) return NLA_ERR_INVALID_DIM; h->slab_kind = value; return NLA_OK; }
+  if (!strcmp(key, "host_macro")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro = value; return NLA_OK; }
+  if (!strcmp(key, "host_macro_mid")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro_mid = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
   if (!strcmp(key, "tc_cg")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_cg = value; return NLA_OK; }
   if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
@@ -1363,6 +1420,9 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "profile")) return h->profile;
   if (!strcmp(key, "macro")) return h->macro;
   if (!strcmp(key, "slab_w")) return h->slab_w;
+  if (!strcmp(key, "slab_kind")) return h->slab_kind;
+  if (!strcmp(key, "host_macro")) return h->host_macro;
+  if (!strcmp(key, "host_macro_mid")) return h->host_macro_mid;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
   if (!strcmp(key, "tc_cg")) return h->tc_cg;
   if (!strcmp(key, "tf32_raw_hi")) return h->tf32_raw_hi;
@@ -1983,7 +2043,9 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   // last download is one chunk (measured on C2 with 4 slabs: 142.3 -> 140.9 ms)
   {
     struct MacroRestore { nla_context* c; int64_t v; ~MacroRestore() { c->macro = v; } } restore{h, h->macro};
-    if (h->macro > 1024) h->macro = 1024;
+    // fused-slab blocks: `host_macro` (1024) at both ends of the diagonal, `host_macro_mid` in between
+    if (h->macro > h->host_macro_mid) h->macro = h->host_macro_mid;
+    if (h->host_macro < h->macro) { D.edge_leaf = h->host_macro; D.edge_span = h->macro; }
     switch (dtype) {
       // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived; in-place multiply)
       case NLA_F64: rc = make_plan<double>(h, D, plan, s_cmp, false, false); break;

@@ -13,6 +13,7 @@ A = (torch.tril(A, -1) + torch.diag(1 + torch.rand(T, dtype=torch.float64, devic
 B0 = (torch.rand(T, m, dtype=torch.float64, device="cuda", generator=g) + 1).t().contiguous().t()
 X = B0.clone(memory_format=torch.preserve_format)
 h.set_option("macro", T); h.set_option("streams", 1)
+if len(sys.argv) > 5: h.set_option("slab_kind", int(sys.argv[5]))
 dbg = torch.zeros(4096, dtype=torch.int64, device="cuda")
 for rep in range(2):
     X.copy_(B0); torch.cuda.synchronize()
@@ -30,7 +31,8 @@ for r in range(nb):
     nxt = st[4 * r + 4] if r + 1 < nb else d
     main, diag, wb = b - a, c - b, d - c
     tot_main += main; tot_diag += diag; tot_wb += wb
-    ideal = r * 128 * 128 * 128 / 64 / 1.965  # ns for r K-blocks at 64 FMA/clk, 1.965 GHz
+    W = int(sys.argv[4]) if len(sys.argv) > 4 else 112
+    ideal = r * 128 * W * 128 / 64 / 1.965  # ns for r K-blocks of a W-vector CTA at 64 FMA/clk, 1.965 GHz
     print(f"row {r:2d}: main {main/1e3:8.1f} us (ideal {ideal/1e3:7.1f}, eff {ideal/max(main,1):.2f})  diag {diag/1e3:6.1f} us  writeback {wb/1e3:5.1f} us")
 print(f"total: main {tot_main/1e3:.1f} us, diag {tot_diag/1e3:.1f} us, writeback {tot_wb/1e3:.1f} us, span {(st[4*nb-1]-t0)/1e3:.1f} us")
 

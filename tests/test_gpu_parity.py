@@ -123,7 +123,7 @@ def test_fused_slab_cutoff_option(nla, gpu, macro):
                 err = rp.error_metric("L", uplo, trans, -1.5, func, A, B0, got)
                 assert rel(got, blas) < 1e-13 and err < 1e-14, (n, m, uplo, trans, func, rel(got, blas), err)
     finally:
-        gpu.set_option("macro", 2048)
+        gpu.set_option("macro", 4096)
 
 
 @pytest.mark.parametrize("leaf", [16, 32, 64, 128])

@@ -425,30 +425,42 @@ def main():
         live_peak = None
     peak = max(FP64_PEAK_TFLOPS, live_peak or 0.0)
 
-    # ---- roofline of the dominant kernel (GEMM update): algorithmic flops / launch-time, from the per-launch events ----
+    # ---- roofline of the dominant kernel: algorithmic flops / launch time, from the per-launch events ----
+    # With enough right-hand sides the whole solve is ONE launch of the row-split fused slab kernel (slab2_f64_kernel: left-looking
+    # DMMA main loop + in-register triangular phase); otherwise the GEMM updates of the recursion dominate.
     gemm = [(f, ms) for k, f, ms in prof if k == 1]
     leafs = [(f, ms) for k, f, ms in prof if k == 0]
     g_fl, g_ms = sum(f for f, _ in gemm), sum(ms for _, ms in gemm)
     l_fl, l_ms = sum(f for f, _ in leafs), sum(ms for _, ms in leafs)
-    top = max(gemm, key=lambda r: r[0]) if gemm else (0.0, 1.0)
-    achieved = g_fl / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else 0.0
+    slab_dominant = l_ms >= g_ms
+    d_fl, d_ms, d_n = (l_fl, l_ms, len(leafs)) if slab_dominant else (g_fl, g_ms, len(gemm))
+    top = max(gemm, key=lambda r: r[0]) if gemm else None
+    achieved = d_fl / (d_ms * 1e-3) * 1e-12 if d_ms > 0 else 0.0
+    tkey = "slab2_f64_kernel_whole_solve" if slab_dominant else "gemm_f64_tma_kernel_top_level"
     traffic, traffic_src = None, "no ncu capture committed"
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of the top-level update from the committed `ncu --set full` capture (per launch)
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed `ncu --set full` capture (per launch)
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic, traffic_src = tj["gemm_f64_tma_kernel_top_level"]["dram_bytes"], tj["gemm_f64_tma_kernel_top_level"]["source"]
+        traffic, traffic_src = tj[tkey]["dram_bytes"], tj[tkey]["source"]
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (FP64 DMMA update, recursion levels above the fused-slab cutoff)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "tensor",
+                "kernel": ("slab2_f64_kernel (row-split fused slab: the whole left-lower solve in one launch, TMA-fed DMMA main loop + in-register substitution)"
+                           if slab_dominant else "gemm_f64_tma_kernel (FP64 DMMA update, recursion levels above the fused-slab cutoff)"),
+                "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "traffic_note": "per launch of the top-level update (M = K = 8192, N = 16384; algorithmic bytes 0.54 GB of A + 1.07 GB of X + 2 x 1.07 GB of the updated block)",
+                "algorithmic_flops_per_launch": d_fl / max(1, d_n),
+                "algorithmic_bytes_note": ("per launch: the lower triangle of A once (1.07 GB) + B read and written once (2 x 2.15 GB) = 5.4 GB; the left-looking kernel "
+                                           "re-reads the solved rows of its own vectors for every block row (L2 / DRAM traffic in `traffic`)"
+                                           if slab_dominant else "per launch of the top-level update (M = K = 8192, N = 16384): 0.54 GB of A + 1.07 GB of X + 2 x 1.07 GB of the updated block"),
                 "peak_source": "FP64 DMMA.8x8x4 issue-rate peak: max(probe constant 37.0 of profiles/r01_probe_dmma_peak.txt, the same microbenchmark run live in this "
                                "process through nla_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2; cuBLAS DGEMM measured 35.4",
                 "peak_measured_this_run": live_peak,
-                "launches_per_step": len(gemm) // prof_steps, "avg_launch_ms": g_ms / max(1, len(gemm)),
-                "flops_per_step": g_fl / prof_steps,
-                "how": "algorithmic flops of all GEMM-update launches / their CUDA-event durations, 2 profiled steps run right after the timed region on one stream",
-                "top_level_launch": {"flops": top[0], "ms": top[1], "tflops": top[0] / (top[1] * 1e-3) * 1e-12},
+                "launches_per_step": d_n // prof_steps, "avg_launch_ms": d_ms / max(1, d_n),
+                "flops_per_step": d_fl / prof_steps,
+                "how": "algorithmic flops of the dominant kernel's launches / their CUDA-event durations, 2 profiled steps run right after the timed region on one stream",
+                "top_level_gemm_launch": ({"flops": top[0], "ms": top[1], "tflops": top[0] / (top[1] * 1e-3) * 1e-12} if top else None),
                 "gemm_share_of_step": g_ms / max(1e-9, g_ms + l_ms), "leaf_share_of_step": l_ms / max(1e-9, g_ms + l_ms),
+                "gemm_tflops": g_fl / (g_ms * 1e-3) * 1e-12 if g_ms > 0 else None,
                 "fused_slab_launches_per_step": len(leafs) // prof_steps,
                 "leaf_tflops": l_fl / (l_ms * 1e-3) * 1e-12 if l_ms > 0 else None,
                 "whole_step_frac_of_peak": value / world / peak}

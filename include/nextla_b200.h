@@ -174,7 +174,13 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
 /* Tunables (the reference hard-codes its thresholds, src/rectrxm.jl:52,63).  Keys:
  *   "leaf"        recursion cutoff = diagonal-block size handled by one leaf launch (default per dtype)
  *   "force_simt"  1 = never use the tensor-core GEMM kernels (debug / A-B comparison)
- *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side; default 4096, 0 = off)
+ *   "macro"       order of the diagonal blocks solved by the fused slab kernel (FP64 left side): -1 (default) = automatic -- the whole
+ *                 diagonal (ONE launch for the call) when the call has at least 48 x #SM right-hand sides, 2048 otherwise, at most one
+ *                 panel in a gated call; 0 = off; any other value = that block order
+ *   "host_stream" 1 (default) = a Float64 left-side solve from host buffers (nla_rectrxm_host) with at least 48 x #SM right-hand sides runs
+ *                 as one streaming launch of the row-split slab kernel: operands arrive chunk by chunk behind device flags, finished
+ *                 chunks are downloaded while the kernel runs; 0 = the chunked multi-launch pipeline
+ *   "host_macro", "host_macro_mid"  chunked host pipeline: fused-slab block order at both ends / in the middle of the diagonal (1024 / 1024)
  *   "slab_kind"   fused FP64 slab kernel: 0 (default) = row-split (the 8 consumer warps share the 128 rows of a block row; CTA width 112 or
  *                 56 vectors, whichever fills the 148 SMs best for the call's number of right-hand sides), 1 = column-split (128 / 64 vectors)
  *   "slab_w"      right-hand-side vectors per CTA of the fused slab kernel: 0 = automatic; 112 / 56 force a width of the row-split kernel,

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <unordered_set>
@@ -53,6 +54,10 @@ struct nla_context {
   int64_t slab_w;       // vectors per CTA of the fused slab kernel: 0 = automatic; 56 / 112 row-split kernel, 64 / 128 column-split kernel
   int64_t slab_kind;    // 0 = row-split kernel (slab2_f64.cuh), 1 = column-split kernel (slab_f64.cuh)
   int64_t host_macro, host_macro_mid;   // host pipeline: fused-slab block order at the ends / in the middle of the diagonal
+  int64_t host_stream;  // 1 = Float64 left-side solves from host buffers run as ONE streaming launch of the row-split slab kernel
+  int* stream_dev; size_t stream_dev_ints;        // device control block of the streaming launch (flag, tables, counters)
+  int* stream_flags_host; int* stream_flags_dev; size_t stream_flags_n;   // host-mapped completion flags (one per output chunk)
+  void* write_value32;  // cuStreamWriteValue32 (driver entry point), or null
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> prof_pool;
@@ -669,6 +674,17 @@ static int launch_slab2_nb(nla_context* ctx, const CUtensorMap& mT, const CUtens
 
 // CTA width of the row-split kernel: the one that finishes the whole call's right-hand sides in the fewest "waves x width" (all RHS
 // slabs of the call run concurrently on their streams): 16384 vectors -> 112 (147 CTAs), 8192 -> 56 (147 CTAs); ties go to the wider CTA.
+static int pick_slab2_width_for(const nla_context* ctx, int64_t m) {   // one launch covering all m vectors
+  if (ctx->slab_w == 56 || ctx->slab_w == 112) return (int)ctx->slab_w;
+  int best_w = 112; int64_t best = -1;
+  for (int w : {112, 56}) {
+    const int64_t ctas = (m + w - 1) / w;
+    const int64_t cost = ((ctas + ctx->sm_count - 1) / ctx->sm_count) * w;
+    if (best < 0 || cost < best) { best = cost; best_w = w; }
+  }
+  return best_w;
+}
+
 static int pick_slab2_width(const nla_context* ctx, const SlabParams& sp) {
   if (ctx->slab_w == 56 || ctx->slab_w == 112) return (int)ctx->slab_w;
   const int64_t nslabs = std::max<int64_t>(1, (sp.m_total + sp.v_count - 1) / std::max(1, sp.v_count));
@@ -917,8 +933,22 @@ static int64_t pick_inv_block(nla_context* ctx, const Problem& P, bool allow) {
   return ib;
 }
 
+// Order of the diagonal blocks the fused FP64 slab kernel takes (option "macro"; -1 = automatic).  The row-split kernel sustains more
+// than the GEMM-based recursion once its CTAs fill the machine (C2: one launch for the whole solve 126.2 ms, cutoff 4096 127.3 ms,
+// 2048 128.6 ms), so with enough right-hand sides the whole diagonal goes to it; with few it only parallelises over the vectors and
+// the recursion (whose GEMMs tile rows as well) keeps the large blocks.  A gated call (A arriving in panels) keeps blocks of at most
+// one panel so that the solve can start before all of A is there.
+static int64_t eff_macro(const nla_context* ctx, const Problem& P, const Gate* gate) {
+  if (ctx->macro >= 0) return ctx->macro;
+  int64_t mac = P.m >= 48ll * ctx->sm_count ? (1ll << 30) : 2048;
+  if (gate) mac = std::min<int64_t>(mac, std::max<int64_t>(2048, gate->panel_cols));
+  return mac;
+}
+
 template <typename T>
-static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_t st, bool allow_inv = true, bool allow_batched = true) {
+static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_t st, bool allow_inv = true, bool allow_batched = true,
+                     int64_t macro = -2) {
+  if (macro == -2) macro = eff_macro(ctx, P, nullptr);
   const int64_t leaf = ctx->leaf > 0 ? std::min<int64_t>(ctx->leaf, LEAF_MAX) : default_leaf(P.dtype);
   std::vector<Op>& ops = plan.ops;
   TmaMaps& maps = plan.maps;
@@ -985,9 +1015,9 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_
   if (tma) {
     const int majT = P.teff_trans ? MAJ_K : MAJ_MN;      // majorness of each matrix in its GEMM role (see launch_update)
     const int majV = !P.right ? MAJ_K : MAJ_MN;
-    if (!P.right && ctx->macro >= 8) {
+    if (!P.right && macro >= 8) {
       // left side: diagonal blocks of order <= macro go to the fused slab kernel
-      build_schedule(P, ctx->macro, 0, P.n, false, true, ops);
+      build_schedule(P, macro, 0, P.n, false, true, ops);
       bool ok = gemm_aligned();
       for (const Op& o : ops)
         if (o.kind == Op::LEAF && ((o.off % 8) || ((o.sz % SL_BM) && (o.off + o.sz != P.n)))) ok = false;
@@ -1150,7 +1180,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
     // is so compute-bound (n flops per element of B) that two transposes of B are noise (n = m = 16384: 2 x 1.3 ms on a 130 ms solve),
     // so the call runs as the left-side problem with the same Teff on a transposed copy of B in the handle's workspace.
     const size_t need = (size_t)P.n * (size_t)P.m * sizeof(double);
-    if (P.right && ctx->right_via_left && !ctx->force_simt && ctx->encode && ctx->macro >= 8 && P.n % 8 == 0 && P.n >= 256 && P.m >= 128 &&
+    if (P.right && ctx->right_via_left && !ctx->force_simt && ctx->encode && ctx->macro != 0 && P.n % 8 == 0 && P.n >= 256 && P.m >= 128 &&
         need <= ((size_t)8 << 30) && tma_ok(P.A, P.n, P.n, P.lda)) {
       WsNeed w{};
       w.bcopy = need;
@@ -1172,7 +1202,7 @@ static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream
     }
   }
   Plan plan;
-  int prc = make_plan<T>(ctx, P, plan, stream);
+  int prc = make_plan<T>(ctx, P, plan, stream, true, true, eff_macro(ctx, P, gate));
   if (prc != NLA_OK) return prc;
   const std::vector<Op>& ops = plan.ops;
   const TmaMaps& maps = plan.maps;
@@ -1328,7 +1358,7 @@ int nla_create(nla_handle_t* handle, int device) {
   nla_context* ctx = new (std::nothrow) nla_context();
   if (!ctx) return NLA_ERR_UNSUPPORTED;
   ctx->magic = NLA_MAGIC; ctx->device = device; ctx->last_cuda = 0; ctx->launches = 0; ctx->encode = nullptr;
-  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = 4096;
+  ctx->leaf = 0; ctx->force_simt = 0; ctx->nstreams = 0; ctx->profile = 0; ctx->macro = -1;
   ctx->tc_bn = 0; ctx->tc_cg = 0; ctx->tf32_raw_hi = 1; ctx->tc_chunk_k = TcCfg<float>::CHUNK_K; ctx->sm_count = 148;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   ctx->stage_a = ctx->stage_b = nullptr; ctx->stage_a_bytes = ctx->stage_b_bytes = 0;
@@ -1339,13 +1369,16 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
+  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0;
+  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
   void* fn = nullptr;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
     ctx->encode = (EncodeTiledFn)fn;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+    ctx->write_value32 = fn;
   if (cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   *handle = ctx;
   return NLA_OK;
@@ -1366,6 +1399,8 @@ int nla_destroy(nla_handle_t h) {
   if (h->stage_b) cudaFree(h->stage_b);
   release_ws(h);
   if (h->lauum_ws) cudaFreeAsync(h->lauum_ws, 0);
+  if (h->stream_dev) cudaFree(h->stream_dev);
+  if (h->stream_flags_host) cudaFreeHost(h->stream_flags_host);
   if (h->cplx_ws) cudaFreeAsync(h->cplx_ws, 0);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
@@ -1383,9 +1418,10 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "leaf")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->leaf = value; return NLA_OK; }
   if (!strcmp(key, "force_simt")) { h->force_simt = value != 0; return NLA_OK; }
   if (!strcmp(key, "profile")) { h->profile = value != 0; return NLA_OK; }
-  if (!strcmp(key, "macro")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
+  if (!strcmp(key, "macro")) { if (value < -1) return NLA_ERR_INVALID_DIM; h->macro = value; return NLA_OK; }
   if (!strcmp(key, "slab_w")) { if (value != 0 && value != 56 && value != 64 && value != 112 && value != 128) return NLA_ERR_INVALID_DIM; h->slab_w = value; return NLA_OK; }
   if (!strcmp(key, "slab_kind")) { if (value < 0 || value > 1) return NLA_ERR_INVALID_DIM; h->slab_kind = value; return NLA_OK; }
+  if (!strcmp(key, "host_stream")) { h->host_stream = value != 0; return NLA_OK; }
   if (!strcmp(key, "host_macro")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro = value; return NLA_OK; }
   if (!strcmp(key, "host_macro_mid")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro_mid = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
@@ -1421,6 +1457,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "macro")) return h->macro;
   if (!strcmp(key, "slab_w")) return h->slab_w;
   if (!strcmp(key, "slab_kind")) return h->slab_kind;
+  if (!strcmp(key, "host_stream")) return h->host_stream;
   if (!strcmp(key, "host_macro")) return h->host_macro;
   if (!strcmp(key, "host_macro_mid")) return h->host_macro_mid;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
@@ -2004,6 +2041,166 @@ static void build_host_plan(bool teff_trans, bool a_lower, bool a_resident, cons
   }
 }
 
+// ---- streaming host pipeline (Float64, left side, solve) ------------------------------------------------------------------------
+// The row-split slab kernel solves the whole problem in ONE launch, block row by block row, left-looking -- so a block row needs only
+// ITS rows of A and B (plus the rows solved before it, which are on the device already).  The host-buffer call therefore becomes:
+//   copy-in stream : the rows of A (referenced trapezoid only) and B chunk by chunk in processing order, a stream-ordered flag write
+//                    (cuStreamWriteValue32; no SM involved) after each chunk;
+//   compute stream : the single kernel; producer / helper / consumer warps wait for the flag of the chunk their block row lives in;
+//   copy-out       : the kernel counts finished (block row, CTA, warp) triples per chunk and raises a host-mapped flag when a chunk is
+//                    final; this (synchronous) call polls the flags in order and queues the download of each chunk at once.
+// Chunks are 128 rows at both ends of the diagonal (the first block row starts after 0.3 ms of copies, the last download is 16 MB) and
+// 256 rows in between.  What stays exposed is physics: the first rows of a forward solve need their share of B long before the
+// flops on them amount to anything, so for about the first third of the diagonal the kernel runs at the speed of the PCIe link
+// (C2: ~4 ms), plus the start and the last download.
+__global__ void set_flag_kernel(int* flag, int value) { if (threadIdx.x == 0) { __threadfence_system(); *flag = value; } }
+
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+static int host_stream_pipeline(nla_handle_t h, const Problem& P, const Problem& D, cudaStream_t s_in, cudaStream_t s_out, cudaStream_t s_cmp) {
+  const int64_t n = P.n, m = P.m;
+  const int nb = (int)((n + SL_BM - 1) / SL_BM);
+  const bool asc = P.lower;   // a solve with a lower Teff walks the diagonal forward
+  // chunk table over the processing order (in block rows): 1 1 2 4 | 8 8 ... | 4 2 1 1
+  std::vector<int> len;
+  if (nb <= 16) len.assign((size_t)nb, 1);
+  else {
+    // (probe hook: NLA_STREAM_CHUNKS="h1,h2,..;mid;t1,t2,.." overrides head / middle / tail chunk lengths in block rows)
+    // measured on C2 (profiles/r02_results/stream_chunks.txt): middle chunks of 2 block rows 132.4 ms, 4: 132.8, 8: 133.8, 16: 137.4
+    // (coarser gating: the kernel waits for rows it does not need yet), 1: 148.6 (1 KB-wide pitched copies starve PCIe)
+    std::vector<int> head = {1, 1, 2}, tail = {2, 1, 1};
+    int midlen = 2;
+    if (const char* e = getenv("NLA_STREAM_CHUNKS")) {
+      std::vector<int> parts[3]; int which = 0, cur = 0; bool have = false;
+      for (const char* c = e;; c++) {
+        if (*c >= '0' && *c <= '9') { cur = cur * 10 + (*c - '0'); have = true; }
+        else { if (have) parts[which].push_back(cur); cur = 0; have = false; if (*c == ';') which = std::min(2, which + 1); if (!*c) break; }
+      }
+      if (!parts[0].empty() && !parts[1].empty() && !parts[2].empty()) { head = parts[0]; midlen = std::max(1, parts[1][0]); tail = parts[2]; }
+    }
+    int hs = 0, ts = 0;
+    for (int v : head) hs += v;
+    for (int v : tail) ts += v;
+    if (hs + ts > nb) { head.assign(1, 1); tail.assign(1, 1); hs = ts = 1; }
+    for (int v : head) len.push_back(v);
+    int mid = nb - hs - ts;
+    while (mid > 0) { len.push_back(std::min(midlen, mid)); mid -= midlen; }
+    for (int v : tail) len.push_back(v);
+  }
+  const int nch = (int)len.size();
+  std::vector<int> ctrl;   // [flag_in][need nb][chunk_of nb][chunk_total nch][done_cnt nch]
+  const int w = pick_slab2_width_for(h, m);
+  const int ctas = (int)((m + w - 1) / w);
+  ctrl.assign((size_t)(1 + 2 * nb + 2 * nch), 0);
+  int* need = ctrl.data() + 1; int* chunk_of = need + nb; int* chunk_total = chunk_of + nb;
+  {
+    int r = 0;
+    for (int c = 0; c < nch; c++) {
+      for (int k = 0; k < len[(size_t)c]; k++, r++) { need[r] = c + 1; chunk_of[r] = c; }
+      chunk_total[c] = len[(size_t)c] * ctas * 8;
+    }
+  }
+  if (h->stream_dev_ints < ctrl.size()) {
+    if (h->stream_dev) cudaFree(h->stream_dev);
+    h->stream_dev = nullptr; h->stream_dev_ints = 0;
+    NLA_CUDA(h, cudaMalloc((void**)&h->stream_dev, ctrl.size() * sizeof(int)));
+    h->stream_dev_ints = ctrl.size();
+  }
+  if (h->stream_flags_n < (size_t)nch) {
+    if (h->stream_flags_host) cudaFreeHost(h->stream_flags_host);
+    h->stream_flags_host = nullptr; h->stream_flags_n = 0;
+    NLA_CUDA(h, cudaHostAlloc((void**)&h->stream_flags_host, (size_t)nch * sizeof(int), cudaHostAllocMapped));
+    NLA_CUDA(h, cudaHostGetDevicePointer((void**)&h->stream_flags_dev, h->stream_flags_host, 0));
+    h->stream_flags_n = (size_t)nch;
+  }
+  volatile int* hflags = h->stream_flags_host;
+  for (int c = 0; c < nch; c++) hflags[c] = 0;
+  int* dctrl = h->stream_dev;
+  cudaEvent_t ctrl_ev = nullptr;
+  NLA_CUDA(h, cudaEventCreateWithFlags(&ctrl_ev, cudaEventDisableTiming));
+  struct EvGuard { cudaEvent_t e; ~EvGuard() { if (e) cudaEventDestroy(e); } } evg{ctrl_ev};
+  NLA_CUDA(h, cudaMemcpyAsync(dctrl, ctrl.data(), ctrl.size() * sizeof(int), cudaMemcpyHostToDevice, s_in));
+  NLA_CUDA(h, cudaEventRecord(ctrl_ev, s_in));
+  NLA_CUDA(h, cudaStreamWaitEvent(s_cmp, ctrl_ev, 0));
+
+  // ---- compute: one launch ----
+  TmaMaps maps;
+  maps.ok = maps.fused = false; maps.tc = false;
+  const int majT = D.teff_trans ? MAJ_K : MAJ_MN;
+  if (!(encode_map(h, &maps.mapT, D.A, n, n, D.lda, majT) && encode_map(h, &maps.mapV112, D.B, n, m, D.ldb, MAJ_K, 112) &&
+        encode_map(h, &maps.mapV56, D.B, n, m, D.ldb, MAJ_K, 56)))
+    return NLA_ERR_UNSUPPORTED;
+  SlabParams sp{};
+  sp.T = (int)n; sp.off = 0; sp.v_base = 0; sp.v_count = (int)m; sp.m_total = m;
+  sp.A = (const double*)D.A; sp.t_rs = D.teff_trans ? D.lda : 1; sp.t_cs = D.teff_trans ? 1 : D.lda;
+  sp.B = (double*)D.B; sp.ldb = D.ldb; sp.beta = P.alpha; sp.post = 1.0; sp.unit = P.unit;
+  sp.flag_in = dctrl; sp.need = dctrl + 1; sp.chunk_of = dctrl + 1 + nb; sp.chunk_total = dctrl + 1 + 2 * nb; sp.done_cnt = dctrl + 1 + 2 * nb + nch;
+  sp.flag_out = h->stream_flags_dev;
+  const int64_t slab_w_saved = h->slab_w;
+  h->slab_w = w;
+  int rc;
+  if (D.teff_trans) rc = asc ? launch_slab2_variant<MAJ_K, true, true>(h, maps, sp, s_cmp) : launch_slab2_variant<MAJ_K, false, true>(h, maps, sp, s_cmp);
+  else rc = asc ? launch_slab2_variant<MAJ_MN, true, true>(h, maps, sp, s_cmp) : launch_slab2_variant<MAJ_MN, false, true>(h, maps, sp, s_cmp);
+  h->slab_w = slab_w_saved;
+  if (rc != NLA_OK) return rc;
+
+  // ---- copy-in: chunk by chunk in processing order, a flag write behind each ----
+  const bool a_lower_stored = (P.lower != P.teff_trans);   // which triangle of the STORED matrix is referenced
+  (void)a_lower_stored;
+  auto chunk_rows = [&](int c, int64_t& R0, int64_t& R1) {   // matrix rows covered by chunk c
+    int r0 = 0;
+    for (int k = 0; k < c; k++) r0 += len[(size_t)k];
+    const int r1 = r0 + len[(size_t)c];
+    if (asc) { R0 = (int64_t)r0 * SL_BM; R1 = std::min<int64_t>(n, (int64_t)r1 * SL_BM); }
+    else { R0 = (int64_t)(nb - r1) * SL_BM; R1 = std::min<int64_t>(n, (int64_t)(nb - r0) * SL_BM); }
+  };
+  const size_t es = 8;
+  for (int c = 0; c < nch; c++) {
+    int64_t R0, R1;
+    chunk_rows(c, R0, R1);
+    // rows [R0, R1) of Teff, columns [0, R1) (lower) or [R0, n) (upper); Teff(r, k) = A[r, k] or A[k, r]
+    const int64_t C0 = P.lower ? 0 : R0, C1 = P.lower ? R1 : n;
+    if (!P.teff_trans) {
+      NLA_CUDA(h, cudaMemcpy2DAsync((char*)D.A + ((size_t)C0 * D.lda + R0) * es, (size_t)D.lda * es, (const char*)P.A + ((size_t)C0 * P.lda + R0) * es,
+                                    (size_t)P.lda * es, (size_t)(R1 - R0) * es, (size_t)(C1 - C0), cudaMemcpyHostToDevice, s_in));
+    } else {
+      NLA_CUDA(h, cudaMemcpy2DAsync((char*)D.A + ((size_t)R0 * D.lda + C0) * es, (size_t)D.lda * es, (const char*)P.A + ((size_t)R0 * P.lda + C0) * es,
+                                    (size_t)P.lda * es, (size_t)(C1 - C0) * es, (size_t)(R1 - R0), cudaMemcpyHostToDevice, s_in));
+    }
+    NLA_CUDA(h, cudaMemcpy2DAsync((char*)D.B + (size_t)R0 * es, (size_t)D.ldb * es, (const char*)P.B + (size_t)R0 * es, (size_t)P.ldb * es,
+                                  (size_t)(R1 - R0) * es, (size_t)m, cudaMemcpyHostToDevice, s_in));
+    if (h->write_value32) {
+      if (((WriteValue32Fn)h->write_value32)((CUstream)s_in, (CUdeviceptr)(uintptr_t)dctrl, (cuuint32_t)(c + 1), 0) != CUDA_SUCCESS) { h->last_cuda = -1; return NLA_ERR_CUDA; }
+    } else {
+      set_flag_kernel<<<1, 32, 0, s_in>>>(dctrl, c + 1);
+      NLA_CUDA(h, cudaGetLastError());
+    }
+  }
+
+  // ---- copy-out: poll the completion flags in order, queue each chunk's download as soon as it is final ----
+  for (int c = 0; c < nch; c++) {
+    unsigned spins = 0;
+    while (hflags[c] == 0) {
+      if ((++spins & 0x3fff) == 0) {
+        const cudaError_t q = cudaStreamQuery(s_cmp);
+        if (q != cudaErrorNotReady && hflags[c] == 0) {   // the kernel is gone (finished or failed) and the chunk was never flagged
+          h->last_cuda = (int)(q == cudaSuccess ? cudaErrorUnknown : q);
+          cudaGetLastError();
+          return NLA_ERR_CUDA;
+        }
+      }
+    }
+    int64_t R0, R1;
+    chunk_rows(c, R0, R1);
+    NLA_CUDA(h, cudaMemcpy2DAsync((char*)P.B + (size_t)R0 * es, (size_t)P.ldb * es, (const char*)D.B + (size_t)R0 * es, (size_t)D.ldb * es,
+                                  (size_t)(R1 - R0) * es, (size_t)m, cudaMemcpyDeviceToHost, s_out));
+  }
+  NLA_CUDA(h, cudaStreamSynchronize(s_out));
+  NLA_CUDA(h, cudaStreamSynchronize(s_cmp));
+  NLA_CUDA(h, cudaStreamSynchronize(s_in));
+  return NLA_OK;
+}
+
 // `A_dev` != nullptr: A is (or is becoming, see `gate`) resident on the device with leading dimension `lda_dev`; only B is staged.
 static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                          const void* A_host, int64_t lda, void* B_host, int64_t ldb, const void* A_dev, int64_t lda_dev, const Gate* gate) {
@@ -2038,19 +2235,22 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   Problem D = P;   // the same problem on the device copies
   D.A = A_dev ? A_dev : h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
   D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
+  // Float64 left-side solve, everything coming from the host: one streaming launch of the row-split slab kernel (see above)
+  if (dtype == NLA_F64 && !P.right && P.solve && !A_dev && !gate && h->host_stream && h->slab_kind == 0 && !h->force_simt && h->encode &&
+      n % 8 == 0 && n >= 256 && m >= 48 * (int64_t)h->sm_count && tma_ok(D.A, n, n, D.lda) && tma_ok(D.B, n, m, D.ldb))
+    return host_stream_pipeline(h, P, D, s_in, s_out, s_cmp);
   Plan plan;
   // Float64: fused-slab blocks of at most 1024 here (2048 on device-resident data): the first leaf can start after one chunk of B and the
   // last download is one chunk (measured on C2 with 4 slabs: 142.3 -> 140.9 ms)
   {
-    struct MacroRestore { nla_context* c; int64_t v; ~MacroRestore() { c->macro = v; } } restore{h, h->macro};
     // fused-slab blocks: `host_macro` (1024) at both ends of the diagonal, `host_macro_mid` in between
-    if (h->macro > h->host_macro_mid) h->macro = h->host_macro_mid;
-    if (h->host_macro < h->macro) { D.edge_leaf = h->host_macro; D.edge_span = h->macro; }
+    int64_t mac = h->macro < 0 ? h->host_macro_mid : std::min(h->macro, h->host_macro_mid);
+    if (h->host_macro < mac) { D.edge_leaf = h->host_macro; D.edge_span = mac; }
     switch (dtype) {
       // (128-wide leaves: a block is prepared right before its leaf, from the tile of A that has just arrived; in-place multiply)
-      case NLA_F64: rc = make_plan<double>(h, D, plan, s_cmp, false, false); break;
-      case NLA_F32: rc = make_plan<float>(h, D, plan, s_cmp, false, false); break;
-      default: rc = make_plan<__half>(h, D, plan, s_cmp, false, false); break;
+      case NLA_F64: rc = make_plan<double>(h, D, plan, s_cmp, false, false, mac); break;
+      case NLA_F32: rc = make_plan<float>(h, D, plan, s_cmp, false, false, mac); break;
+      default: rc = make_plan<__half>(h, D, plan, s_cmp, false, false, mac); break;
     }
   }
   if (rc != NLA_OK) return rc;

@@ -81,6 +81,7 @@ slab2_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
       int kt = 0;
       for (int r = 0; r < nb; r++) {
         const int i = ASC ? r : nb - 1 - r;
+        if (p.flag_in) slab_wait_flag(p.flag_in, p.need[r]);   // streaming mode: this block row's rows of A have landed
         const int cnt = kcount(i);
         for (int jj = 0; jj < cnt; jj++) {
           const int j = kblock(i, jj);
@@ -122,6 +123,7 @@ slab2_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
       for (int r = 0; r < nb; r++) {
         const int i = ASC ? r : nb - 1 - r;
         if (r >= 2) mbar_wait(smem_u32(&lp_empty[r & 1]), ((r >> 1) - 1) & 1);
+        if (p.flag_in) { if (lane == 0) slab_wait_flag(p.flag_in, p.need[r]); __syncwarp(); }
         double* lpw = lp_base + (r & 1) * SL_LP_DOUBLES;
         const int vr = min(SL_BM, p.T - i * SL_BM);
         const long long base = (long long)p.off + i * SL_BM;
@@ -231,6 +233,7 @@ slab2_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
     double* Bblk = p.B + (long long)(p.off + rbase);
 
     if (SOLVE) {
+      if (p.flag_in) { if (lane == 0) slab_wait_flag(p.flag_in, p.need[r]); __syncwarp(); }   // streaming mode: this block row of B has landed
       // rhs = beta*B - S
 #pragma unroll
       for (int jn = 0; jn < NB; jn++)
@@ -360,6 +363,15 @@ slab2_f64_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant
       fence_proxy_async_all();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&xdone_bar));
+      if (p.flag_out && lane == 0) {
+        // streaming mode: the warp whose arrival completes an output chunk (all its block rows, every CTA, every consumer warp -- each
+        // of them fenced its stores above) tells the host that the chunk may be downloaded
+        const int c = p.chunk_of[r];
+        if (atomicAdd(p.done_cnt + c, 1) == p.chunk_total[c] - 1) {
+          __threadfence_system();
+          p.flag_out[c] = 1;
+        }
+      }
     }
     NLA_SLAB2_STAMP(4 * r + 3);
   }

@@ -56,7 +56,23 @@ struct SlabParams {
   double beta, post;
   int unit;               // 1: unit diagonal (the stored diagonal is not used)
   unsigned long long* dbg;   // probes only (option tc_dbg): 4 globaltimer stamps per block row from warp 0 of CTA 0
+  // Streaming mode of the row-split kernel (host-buffer pipeline, nla_api.cu host_stream_pipeline): the operands are still ARRIVING from
+  // the host while the kernel runs and finished rows LEAVE while it runs.  All null / zero for device-resident calls.
+  const int* flag_in;        // device word, bumped (stream-ordered, after the copies) every time another chunk of A and B has landed
+  const int* need;           // [block row in processing order] value flag_in must have reached before that block row may start
+  const int* chunk_of;       // [block row in processing order] output chunk the block row belongs to
+  const int* chunk_total;    // [chunk] warp arrivals that complete the chunk (= its block rows x CTAs x consumer warps)
+  int* done_cnt;             // [chunk] arrival counters (zeroed by the host)
+  volatile int* flag_out;    // [chunk] host-mapped words: set to 1 when the chunk is final in device memory (the host then downloads it)
 };
+
+// streaming mode: spin until *flag >= need (acquire: data copied in before the flag was bumped is visible afterwards)
+__device__ __forceinline__ void slab_wait_flag(const int* flag, int need) {
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  } while (v < need);
+}
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 

@@ -192,3 +192,44 @@ def test_single_process_multi_gpu_entry(nla, gpu, dtype):
         assert torch.cuda.current_device() == 0
     finally:
         mg.close()
+
+
+@pytest.mark.parametrize("uplo,trans", [("L", "N"), ("U", "N"), ("L", "T"), ("U", "T")])
+def test_streaming_host_pipeline(nla, gpu, uplo, trans):
+    """nla_rectrxm_host, Float64 left-side solve with enough right-hand sides to fill the machine: ONE streaming launch of the
+    row-split slab kernel (operands arrive chunk by chunk behind device flags, finished chunks are downloaded while the kernel
+    runs).  Forward and backward walks of the diagonal, stored / transposed A, ragged order (not a multiple of 128), alpha != 1,
+    pinned and pageable buffers; result against OpenBLAS and bit-identical to the same kernel on device-resident data."""
+    import torch
+
+    n, m = 2184, 7168
+    A, B0 = rp.make_inputs(n, m, "L", uplo, np.float64, seed=77, recipe="scaled")
+    want = rp.blas_reference("L", uplo, trans, 1.25, "S", A, B0)
+    gpu.launch_count(reset=True)
+    B = B0.copy(order="F")
+    nla.unified_rectrxm_host("L", uplo, trans, 1.25, "S", A, B, handle=gpu)
+    assert gpu.launch_count() == 1                                   # the whole solve is one kernel
+    assert np.linalg.norm(B - want) / np.linalg.norm(want) < 1e-13
+    assert rp.error_metric("L", uplo, trans, 1.25, "S", A, B0, B) < 1e-14
+    # pinned buffers, and the same kernel on resident data (macro >= n: one fused-slab launch)
+    hA = torch.from_numpy(np.ascontiguousarray(A.T)).pin_memory()
+    hB = torch.from_numpy(np.ascontiguousarray(B0.T)).pin_memory()
+    rc = nla.load_library().nla_rectrxm_host(gpu._h, b"L", uplo.encode(), trans.encode(), b"S", 0, n, m, 1.25, hA.data_ptr(), n, hB.data_ptr(), n)
+    assert rc == 0
+    assert np.array_equal(np.asfortranarray(hB.numpy().T), B)
+    gpu.set_option("macro", 4096); gpu.set_option("streams", 1)
+    try:
+        dA, dB = nla.colmajor(A), nla.colmajor(B0)
+        nla.unified_rectrxm("L", uplo, trans, 1.25, "S", dA, dB, handle=gpu)
+        torch.cuda.synchronize()
+        assert np.array_equal(nla.to_numpy(dB), B)
+    finally:
+        gpu.set_option("macro", -1); gpu.set_option("streams", 0)
+    # the chunked pipeline (option host_stream = 0) must agree to rounding
+    gpu.set_option("host_stream", 0)
+    try:
+        B2 = B0.copy(order="F")
+        nla.unified_rectrxm_host("L", uplo, trans, 1.25, "S", A, B2, handle=gpu)
+    finally:
+        gpu.set_option("host_stream", 1)
+    assert np.linalg.norm(B2 - B) / np.linalg.norm(B) < 1e-13

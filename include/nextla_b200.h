@@ -180,6 +180,10 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *   "host_stream" 1 (default) = a Float64 left-side solve from host buffers (nla_rectrxm_host) with at least 48 x #SM right-hand sides runs
  *                 as one streaming launch of the row-split slab kernel: operands arrive chunk by chunk behind device flags, finished
  *                 chunks are downloaded while the kernel runs; 0 = the chunked multi-launch pipeline
+ *   "gated_stream" 0 (default); 1 = nla_rectrxm_gated runs a Float64 left-side solve with at least 48 x #SM right-hand sides as one launch too,
+ *                 every block row waiting on a device word that counts the arrived panels.  ONLY safe when the panels are delivered by
+ *                 copy engines / peer DMA: the kernel occupies every SM while it waits, so SM-based collectives (NCCL kernels) queued
+ *                 behind it never start
  *   "host_macro", "host_macro_mid"  chunked host pipeline: fused-slab block order at both ends / in the middle of the diagonal (1024 / 1024)
  *   "slab_kind"   fused FP64 slab kernel: 0 (default) = row-split (the 8 consumer warps share the 128 rows of a block row; CTA width 112 or
  *                 56 vectors, whichever fills the 148 SMs best for the call's number of right-hand sides), 1 = column-split (128 / 64 vectors)

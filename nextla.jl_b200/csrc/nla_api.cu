@@ -55,7 +55,8 @@ struct nla_context {
   int64_t slab_kind;    // 0 = row-split kernel (slab2_f64.cuh), 1 = column-split kernel (slab_f64.cuh)
   int64_t host_macro, host_macro_mid;   // host pipeline: fused-slab block order at the ends / in the middle of the diagonal
   int64_t host_stream;  // 1 = Float64 left-side solves from host buffers run as ONE streaming launch of the row-split slab kernel
-  int* stream_dev; size_t stream_dev_ints;        // device control block of the streaming launch (flag, tables, counters)
+  int64_t gated_stream; // 1 = gated Float64 left-side solves too (only safe when the panels arrive without using SMs)
+  int* stream_dev; size_t stream_dev_ints; int stream_dev_async;   // device control block of the streaming launch (flag, tables, counters)
   int* stream_flags_host; int* stream_flags_dev; size_t stream_flags_n;   // host-mapped completion flags (one per output chunk)
   void* write_value32;  // cuStreamWriteValue32 (driver entry point), or null
   struct ProfRec { int kind; double flops; cudaEvent_t e0, e1; };
@@ -1173,9 +1174,87 @@ __global__ void __launch_bounds__(256) transpose_f64_kernel(const double* __rest
     if (c0 + tx < cols && r0 + j < rows) dst[(c0 + tx) + (r0 + j) * ldd] = tile[tx][j];
 }
 
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+// Gated Float64 left-side solve with enough right-hand sides (multi-GPU: A is arriving in column panels): still ONE launch of the
+// row-split slab kernel.  A small side stream waits for the panel events in consumption order and bumps a device word after each
+// (cuStreamWriteValue32); block row r of the kernel waits until the panels that hold its part of Teff have been counted.
+static int gated_stream_solve(nla_context* ctx, const Problem& P, cudaStream_t stream, const Gate* gate) {
+  const int64_t n = P.n, m = P.m;
+  const int nb = (int)((n + SL_BM - 1) / SL_BM);
+  const bool asc = P.lower;
+  const int64_t pc = gate->panel_cols, np = (n + pc - 1) / pc;
+  // panels in consumption order: ascending for a forward walk of the diagonal, descending otherwise (= nla_panel_order for a solve)
+  std::vector<int> ctrl((size_t)(1 + nb), 0);
+  for (int r = 0; r < nb; r++) {
+    const int i = asc ? r : nb - 1 - r;
+    // block row i reads Teff[i, 0..i] (lower) or Teff[i, i..] (upper); in A's storage those are the columns (or, for a transposed
+    // Teff, the rows -- which live in ALL column panels up to the same bound by symmetry of the index ranges) [lo, hi)
+    const int64_t lo = P.lower ? 0 : (int64_t)i * SL_BM, hi = P.lower ? std::min<int64_t>(n, (int64_t)(i + 1) * SL_BM) : n;
+    int64_t need;
+    if (!P.teff_trans) need = asc ? (hi - 1) / pc + 1 : np - lo / pc;          // column panels [0, hi) arrived first / [lo, n) arrived first
+    else {
+      // Teff(r, k) = A[k, r]: block row i lives in the COLUMNS [128 i, 128 i + 128) of A, rows lo..hi: one or two panels, which arrive
+      // in the same monotone order
+      const int64_t c0 = (int64_t)i * SL_BM, c1 = std::min<int64_t>(n, c0 + SL_BM);
+      need = asc ? (c1 - 1) / pc + 1 : np - c0 / pc;
+    }
+    ctrl[(size_t)(1 + r)] = (int)std::min<int64_t>(need, np);
+  }
+  const size_t ints = ctrl.size();
+  // the control block is allocated with cudaMalloc at nla_create (stream memory operations do not accept stream-ordered pool memory)
+  if (ctx->stream_dev_ints < ints) return NLA_ERR_UNSUPPORTED;
+  int* dctrl = ctx->stream_dev;
+  NLA_CUDA(ctx, cudaMemcpyAsync(dctrl, ctrl.data(), ints * sizeof(int), cudaMemcpyHostToDevice, stream));
+  if (!ctx->prep_stream) {
+    NLA_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    NLA_CUDA(ctx, cudaEventCreateWithFlags(&ctx->prep_event, cudaEventDisableTiming));
+  }
+  NLA_CUDA(ctx, cudaEventRecord(ctx->fork_event, stream));
+  NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, ctx->fork_event, 0));
+  for (int64_t k = 0; k < np; k++) {
+    const int64_t p = asc ? k : np - 1 - k;
+    NLA_CUDA(ctx, cudaStreamWaitEvent(ctx->prep_stream, gate->events[p], 0));
+    if (((WriteValue32Fn)ctx->write_value32)((CUstream)ctx->prep_stream, (CUdeviceptr)(uintptr_t)dctrl, (cuuint32_t)(k + 1), 0) != CUDA_SUCCESS) {
+      ctx->last_cuda = -1;
+      return NLA_ERR_CUDA;
+    }
+  }
+  TmaMaps maps;
+  maps.ok = maps.fused = false; maps.tc = false;
+  const int majT = P.teff_trans ? MAJ_K : MAJ_MN;
+  if (!(encode_map(ctx, &maps.mapT, P.A, n, n, P.lda, majT) && encode_map(ctx, &maps.mapV112, P.B, n, m, P.ldb, MAJ_K, 112) &&
+        encode_map(ctx, &maps.mapV56, P.B, n, m, P.ldb, MAJ_K, 56)))
+    return NLA_ERR_UNSUPPORTED;
+  SlabParams sp{};
+  sp.T = (int)n; sp.off = 0; sp.v_base = 0; sp.v_count = (int)m; sp.m_total = m;
+  sp.A = (const double*)P.A; sp.t_rs = P.teff_trans ? P.lda : 1; sp.t_cs = P.teff_trans ? 1 : P.lda;
+  sp.B = (double*)P.B; sp.ldb = P.ldb; sp.beta = P.alpha; sp.post = 1.0; sp.unit = P.unit;
+  sp.flag_in = dctrl; sp.need = dctrl + 1;
+  NvtxRange r(ctx, "nla gated one-launch solve n=%lld m=%lld", (long long)n, (long long)m);
+  int rc;
+  if (P.teff_trans) rc = asc ? launch_slab2_variant<MAJ_K, true, true>(ctx, maps, sp, stream) : launch_slab2_variant<MAJ_K, false, true>(ctx, maps, sp, stream);
+  else rc = asc ? launch_slab2_variant<MAJ_MN, true, true>(ctx, maps, sp, stream) : launch_slab2_variant<MAJ_MN, false, true>(ctx, maps, sp, stream);
+  if (rc != NLA_OK) return rc;
+  // the flag stream must be drained before a later call reuses the control block: join it into the caller's stream
+  NLA_CUDA(ctx, cudaEventRecord(ctx->prep_event, ctx->prep_stream));
+  NLA_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->prep_event, 0));
+  return NLA_OK;
+}
+
 template <typename T>
 static int rectrxm_typed(nla_context* ctx, const Problem& P, cudaStream_t stream, const Gate* gate = nullptr) {
   if constexpr (std::is_same<T, double>::value) {
+    // (opt-in, option "gated_stream": the one-launch kernel fills every SM and SPINS on the panel flags, so it is only safe when the
+    //  panels are delivered WITHOUT SMs -- copy engines, peer DMA.  NCCL's broadcast kernels need SMs of their own: behind a resident
+    //  spinning grid they never start, and the solve deadlocks (observed at 2 GPUs).  The default gated path below keeps blocks of at
+    //  most one panel instead.)
+    if (gate && ctx->gated_stream && P.solve && !P.right && ctx->macro < 0 && ctx->host_stream && ctx->slab_kind == 0 && !ctx->force_simt && ctx->encode && ctx->write_value32 &&
+        P.n % 8 == 0 && P.n >= 256 && P.m >= 48ll * ctx->sm_count && tma_ok(P.A, P.n, P.n, P.lda) && tma_ok(P.B, P.n, P.m, P.ldb))
+    {
+      const int grc = gated_stream_solve(ctx, P, stream, gate);
+      if (grc != NLA_ERR_UNSUPPORTED) return grc;   // (order too large for the control block: the panel-capped schedule below)
+    }
     // FP64, right side: X op(A) = alpha B  <=>  op(A)^T X^T = alpha B^T.  The fused slab kernel exists for the left side only, and FP64
     // is so compute-bound (n flops per element of B) that two transposes of B are noise (n = m = 16384: 2 x 1.3 ms on a 130 ms solve),
     // so the call runs as the left-side problem with the same Teff on a transposed copy of B in the handle's workspace.
@@ -1369,7 +1448,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0;
+  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
   ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
@@ -1379,6 +1458,9 @@ int nla_create(nla_handle_t* handle, int device) {
     ctx->encode = (EncodeTiledFn)fn;
   if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
     ctx->write_value32 = fn;
+  // control block of the streaming launches (device flag word + per-block-row tables): 64 Ki ints, enough for n <= 2 M
+  if (cudaMalloc((void**)&ctx->stream_dev, (size_t)(1 << 16) * sizeof(int)) == cudaSuccess) ctx->stream_dev_ints = 1 << 16;
+  else { cudaGetLastError(); ctx->stream_dev = nullptr; }
   if (cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   *handle = ctx;
   return NLA_OK;
@@ -1399,7 +1481,7 @@ int nla_destroy(nla_handle_t h) {
   if (h->stage_b) cudaFree(h->stage_b);
   release_ws(h);
   if (h->lauum_ws) cudaFreeAsync(h->lauum_ws, 0);
-  if (h->stream_dev) cudaFree(h->stream_dev);
+  if (h->stream_dev) { if (h->stream_dev_async) cudaFreeAsync(h->stream_dev, 0); else cudaFree(h->stream_dev); }
   if (h->stream_flags_host) cudaFreeHost(h->stream_flags_host);
   if (h->cplx_ws) cudaFreeAsync(h->cplx_ws, 0);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
@@ -1422,6 +1504,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "slab_w")) { if (value != 0 && value != 56 && value != 64 && value != 112 && value != 128) return NLA_ERR_INVALID_DIM; h->slab_w = value; return NLA_OK; }
   if (!strcmp(key, "slab_kind")) { if (value < 0 || value > 1) return NLA_ERR_INVALID_DIM; h->slab_kind = value; return NLA_OK; }
   if (!strcmp(key, "host_stream")) { h->host_stream = value != 0; return NLA_OK; }
+  if (!strcmp(key, "gated_stream")) { h->gated_stream = value != 0; return NLA_OK; }
   if (!strcmp(key, "host_macro")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro = value; return NLA_OK; }
   if (!strcmp(key, "host_macro_mid")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro_mid = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
@@ -1458,6 +1541,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "slab_w")) return h->slab_w;
   if (!strcmp(key, "slab_kind")) return h->slab_kind;
   if (!strcmp(key, "host_stream")) return h->host_stream;
+  if (!strcmp(key, "gated_stream")) return h->gated_stream;
   if (!strcmp(key, "host_macro")) return h->host_macro;
   if (!strcmp(key, "host_macro_mid")) return h->host_macro_mid;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;
@@ -2053,10 +2137,6 @@ static void build_host_plan(bool teff_trans, bool a_lower, bool a_resident, cons
 // 256 rows in between.  What stays exposed is physics: the first rows of a forward solve need their share of B long before the
 // flops on them amount to anything, so for about the first third of the diagonal the kernel runs at the speed of the PCIe link
 // (C2: ~4 ms), plus the start and the last download.
-__global__ void set_flag_kernel(int* flag, int value) { if (threadIdx.x == 0) { __threadfence_system(); *flag = value; } }
-
-typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-
 static int host_stream_pipeline(nla_handle_t h, const Problem& P, const Problem& D, cudaStream_t s_in, cudaStream_t s_out, cudaStream_t s_cmp) {
   const int64_t n = P.n, m = P.m;
   const int nb = (int)((n + SL_BM - 1) / SL_BM);
@@ -2101,8 +2181,8 @@ static int host_stream_pipeline(nla_handle_t h, const Problem& P, const Problem&
     }
   }
   if (h->stream_dev_ints < ctrl.size()) {
-    if (h->stream_dev) cudaFree(h->stream_dev);
-    h->stream_dev = nullptr; h->stream_dev_ints = 0;
+    if (h->stream_dev) { if (h->stream_dev_async) cudaFreeAsync(h->stream_dev, 0); else cudaFree(h->stream_dev); }
+    h->stream_dev = nullptr; h->stream_dev_ints = 0; h->stream_dev_async = 0;
     NLA_CUDA(h, cudaMalloc((void**)&h->stream_dev, ctrl.size() * sizeof(int)));
     h->stream_dev_ints = ctrl.size();
   }
@@ -2169,12 +2249,8 @@ static int host_stream_pipeline(nla_handle_t h, const Problem& P, const Problem&
     }
     NLA_CUDA(h, cudaMemcpy2DAsync((char*)D.B + (size_t)R0 * es, (size_t)D.ldb * es, (const char*)P.B + (size_t)R0 * es, (size_t)P.ldb * es,
                                   (size_t)(R1 - R0) * es, (size_t)m, cudaMemcpyHostToDevice, s_in));
-    if (h->write_value32) {
-      if (((WriteValue32Fn)h->write_value32)((CUstream)s_in, (CUdeviceptr)(uintptr_t)dctrl, (cuuint32_t)(c + 1), 0) != CUDA_SUCCESS) { h->last_cuda = -1; return NLA_ERR_CUDA; }
-    } else {
-      set_flag_kernel<<<1, 32, 0, s_in>>>(dctrl, c + 1);
-      NLA_CUDA(h, cudaGetLastError());
-    }
+    // (a stream memory operation, not a kernel: the solve occupies every SM while it waits, a flag-setting kernel might never be scheduled)
+    if (((WriteValue32Fn)h->write_value32)((CUstream)s_in, (CUdeviceptr)(uintptr_t)dctrl, (cuuint32_t)(c + 1), 0) != CUDA_SUCCESS) { h->last_cuda = -1; return NLA_ERR_CUDA; }
   }
 
   // ---- copy-out: poll the completion flags in order, queue each chunk's download as soon as it is final ----
@@ -2236,7 +2312,7 @@ static int host_pipeline(nla_handle_t h, char side, char uplo, char trans, char 
   D.A = A_dev ? A_dev : h->stage_a; D.lda = dlda; D.B = h->stage_b; D.ldb = dldb;
   D.es = P.right ? dldb : 1; D.vs = P.right ? 1 : dldb;
   // Float64 left-side solve, everything coming from the host: one streaming launch of the row-split slab kernel (see above)
-  if (dtype == NLA_F64 && !P.right && P.solve && !A_dev && !gate && h->host_stream && h->slab_kind == 0 && !h->force_simt && h->encode &&
+  if (dtype == NLA_F64 && !P.right && P.solve && !A_dev && !gate && h->host_stream && h->write_value32 && h->slab_kind == 0 && !h->force_simt && h->encode &&
       n % 8 == 0 && n >= 256 && m >= 48 * (int64_t)h->sm_count && tma_ok(D.A, n, n, D.lda) && tma_ok(D.B, n, m, D.ldb))
     return host_stream_pipeline(h, P, D, s_in, s_out, s_cmp);
   Plan plan;

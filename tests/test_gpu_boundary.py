@@ -233,3 +233,43 @@ def test_streaming_host_pipeline(nla, gpu, uplo, trans):
     finally:
         gpu.set_option("host_stream", 1)
     assert np.linalg.norm(B2 - B) / np.linalg.norm(B) < 1e-13
+
+
+@pytest.mark.parametrize("uplo,trans", [("L", "N"), ("U", "N"), ("L", "T"), ("U", "T")])
+def test_gated_one_launch_solve(nla, gpu, uplo, trans):
+    """nla_rectrxm_gated, Float64 left-side solve with enough right-hand sides: A arrives in column panels (here copied on a side
+    stream, each panel behind a spin kernel, the rest of A NaN until then) and the solve is still ONE launch of the row-split slab
+    kernel -- a side stream counts the panel events into a device word, every block row waits for the panels that hold its part of A.
+    Result bit-identical to the plain call."""
+    import torch
+
+    n, m, pc = 2048, 7168, 256
+    A, B0 = rp.make_inputs(n, m, "L", uplo, np.float64, seed=61, recipe="scaled")
+    dA_full = nla.colmajor(A)
+    dB = nla.colmajor(B0)
+    nla.unified_rectrxm("L", uplo, trans, 1.25, "S", dA_full, dB, handle=gpu)
+    torch.cuda.synchronize()
+    want = nla.to_numpy(dB)
+    assert rp.error_metric("L", uplo, trans, 1.25, "S", A, B0, want) < 1e-14
+    dA = torch.full_like(dA_full, float("nan"))
+    dB = nla.colmajor(B0)
+    order = nla.panel_order("L", uplo, trans, "S", n, pc)
+    side_stream = torch.cuda.Stream()
+    events = [torch.cuda.Event() for _ in range(n // pc)]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side_stream):
+        torch.cuda._sleep(40_000_000)      # ~20 ms before the first panel: the kernel is resident and really has to wait
+        for p in order:
+            dA[:, p * pc:(p + 1) * pc].copy_(dA_full[:, p * pc:(p + 1) * pc])
+            events[p].record(side_stream)
+    gpu.set_option("gated_stream", 1)   # opt-in: safe here, the panels arrive through the copy engine
+    try:
+        gpu.launch_count(reset=True)
+        nla.unified_rectrxm_gated("L", uplo, trans, 1.25, "S", dA, dB, pc, events, handle=gpu)
+        assert gpu.launch_count() == 1
+        torch.cuda.synchronize()
+    finally:
+        gpu.set_option("gated_stream", 0)
+    got = nla.to_numpy(dB)
+    assert np.isfinite(got).all()
+    assert np.array_equal(got, want), (uplo, trans)

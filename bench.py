@@ -334,6 +334,8 @@ def main():
     nla = ge.load_package()
     h = nla.Handle(local)
     h.set_option("streams", args.streams)
+    if os.environ.get("NLA_GATED_MACRO"):
+        h.set_option("gated_macro", int(os.environ["NLA_GATED_MACRO"]))
 
     n, m = args.n, args.m
     dt = torch.float64

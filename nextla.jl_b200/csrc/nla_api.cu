@@ -56,6 +56,7 @@ struct nla_context {
   int64_t host_macro, host_macro_mid;   // host pipeline: fused-slab block order at the ends / in the middle of the diagonal
   int64_t host_stream;  // 1 = Float64 left-side solves from host buffers run as ONE streaming launch of the row-split slab kernel
   int64_t gated_stream; // 1 = gated Float64 left-side solves too (only safe when the panels arrive without using SMs)
+  int64_t gated_macro;  // fused-slab block order of a gated call (at least one panel)
   int* stream_dev; size_t stream_dev_ints; int stream_dev_async;   // device control block of the streaming launch (flag, tables, counters)
   int* stream_flags_host; int* stream_flags_dev; size_t stream_flags_n;   // host-mapped completion flags (one per output chunk)
   void* write_value32;  // cuStreamWriteValue32 (driver entry point), or null
@@ -942,7 +943,7 @@ static int64_t pick_inv_block(nla_context* ctx, const Problem& P, bool allow) {
 static int64_t eff_macro(const nla_context* ctx, const Problem& P, const Gate* gate) {
   if (ctx->macro >= 0) return ctx->macro;
   int64_t mac = P.m >= 48ll * ctx->sm_count ? (1ll << 30) : 2048;
-  if (gate) mac = std::min<int64_t>(mac, std::max<int64_t>(2048, gate->panel_cols));
+  if (gate) mac = std::min<int64_t>(mac, std::max<int64_t>(ctx->gated_macro, gate->panel_cols));
   return mac;
 }
 
@@ -1448,7 +1449,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& s : ctx->host_streams) s = nullptr;
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
-  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
+  ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->gated_macro = 2048; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
   ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
@@ -1505,6 +1506,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "slab_kind")) { if (value < 0 || value > 1) return NLA_ERR_INVALID_DIM; h->slab_kind = value; return NLA_OK; }
   if (!strcmp(key, "host_stream")) { h->host_stream = value != 0; return NLA_OK; }
   if (!strcmp(key, "gated_stream")) { h->gated_stream = value != 0; return NLA_OK; }
+  if (!strcmp(key, "gated_macro")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->gated_macro = value; return NLA_OK; }
   if (!strcmp(key, "host_macro")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro = value; return NLA_OK; }
   if (!strcmp(key, "host_macro_mid")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro_mid = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
@@ -1542,6 +1544,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "slab_kind")) return h->slab_kind;
   if (!strcmp(key, "host_stream")) return h->host_stream;
   if (!strcmp(key, "gated_stream")) return h->gated_stream;
+  if (!strcmp(key, "gated_macro")) return h->gated_macro;
   if (!strcmp(key, "host_macro")) return h->host_macro;
   if (!strcmp(key, "host_macro_mid")) return h->host_macro_mid;
   if (!strcmp(key, "tc_bn")) return h->tc_bn;

@@ -148,6 +148,20 @@ int nla_memcpy2d_async(nla_handle_t handle, void *dst, int64_t dst_pitch_bytes, 
 int nla_laswp(nla_handle_t handle, int dtype, int64_t rows, int64_t ncols, void *A, int64_t lda, int64_t k1, int64_t k2,
               const int64_t *ipiv, int incx, void *stream);
 
+/* getrf2!(A, ipiv, info)                                                                  -- src/lu.jl:185-299
+ * Recursive LU with partial pivoting of a device matrix, A = P * L * U, every step on the device: the reference's recursion on the
+ * columns (split at min(m, n) / 2, :253-256) with laswp (:274, :298), the unit-lower recursive TRSM (:277) and the GEMM update (:280) of
+ * this library, and a cooperative panel kernel (getrf.cuh) for blocks of <= 32 columns that applies the reference's single-column rule
+ * (:224-251): pivot = first entry of largest magnitude, interchange, scale by the reciprocal (divide when |pivot| < sfmin), a zero pivot
+ * leaves the column alone and is reported.
+ *   A     m x n, column-major, leading dimension lda >= max(1, m); overwritten by L (unit diagonal not stored) and U
+ *   ipiv  DEVICE vector of min(m, n) int64, 1-based: row i was interchanged with row ipiv[i] (the reference's Vector{Int})
+ *   info  DEVICE int: 0, or i if U[i, i] is exactly zero (first such i); the reference returns it, a device-side caller reads it after
+ *         synchronising the stream.  Asynchronous: no host synchronisation inside.
+ * NLA_F64 and NLA_F32 (the reference's real BlasFloat types); NLA_F16 and the complex types return NLA_ERR_UNSUPPORTED.
+ * Illegal sizes (m < 0, n < 0, lda < max(1, m); the reference's info = -1 / -2 / -4, :192-203) return NLA_ERR_INVALID_DIM. */
+int nla_getrf2(nla_handle_t handle, int dtype, int64_t m, int64_t n, void *A, int64_t lda, int64_t *ipiv, int *info, void *stream);
+
 /* lauum!(uplo, n, A, ib)                                                                 -- src/lauum.jl:52-186
  * A := L^H * L (uplo 'L') or U * U^H (uplo 'U') on a device matrix: the triangular factor is stored in the `uplo` triangle of A, the
  * result replaces it in the same triangle; the opposite triangle is neither used nor written (the reference multiplies whole diagonal

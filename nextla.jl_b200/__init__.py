@@ -11,6 +11,7 @@ Function names and argument order follow the reference:
   GEMM_ADD(A, B, C)  (C += A*B),  GEMM_SUB(A, B, C)  (A -= B*C) <- src/matmul.jl:69-81
   trsm(side, uplo, transa, diag, A, B, alpha), trmm(...)       <- src/trsm.jl:186-205, src/trmm.jl:430-448
   laswp(A, first, last, ipiv, incx), getrf2_update(A, n1, ipiv) <- src/lu.jl:470-530, :274-280 (the device steps of the recursive LU)
+  getrf2(A)                                                     <- src/lu.jl:185-299 (the whole recursive LU on the device, nla_getrf2)
   lauum(uplo, A, ib)                                            <- src/lauum.jl:52-186 (block loop; O(n^3) steps on this library's kernels)
 
 Matrices are column-major device arrays: 2-D torch CUDA tensors with stride (1, ld) (use `colmajor()` /
@@ -76,6 +77,7 @@ def load_library():
         "nla_rectrxm_hostb_gated": (I, [H, CH, CH, CH, CH, I, L, L, D, P, L, P, L, L, L, c.POINTER(c.c_void_p)]),
         "nla_memcpy2d_async": (I, [H, P, L, P, L, L, L, I, P]),
         "nla_laswp": (I, [H, I, L, L, P, L, L, L, P, I, P]),
+        "nla_getrf2": (I, [H, I, L, L, P, L, P, P, P]),
         "nla_panel_order": (L, [CH, CH, CH, CH, L, L, c.POINTER(c.c_int64), L]),
         "nla_trsm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
         "nla_trmm_leaf": (I, [H, CH, CH, I, L, L, P, L, P, L, P]),
@@ -98,7 +100,7 @@ def load_library():
 
 def exported_symbols():
     return ["nla_create", "nla_destroy", "nla_status_string", "nla_last_cuda_error", "nla_version", "nla_rectrxm", "nla_rectrxm_host",
-            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak", "nla_lauum", "nla_rectrxm_complex",
+            "nla_workspace_bytes", "nla_reserve", "nla_set_workspace", "nla_probe_fp64_peak", "nla_lauum", "nla_getrf2", "nla_rectrxm_complex",
             "nla_mg_create", "nla_mg_destroy", "nla_mg_device_count", "nla_mg_handle", "nla_mg_stream", "nla_mg_last_nccl_error", "nla_mg_sync",
             "nla_mg_rectrxm", "nla_mg_rectrxm_host",
             "nla_rectrxm_gated", "nla_rectrxm_hostb_gated", "nla_panel_order", "nla_trxm", "nla_memcpy2d_async", "nla_laswp", "nla_host_plan",
@@ -431,6 +433,28 @@ def getrf2_update(A, n1: int, ipiv, **kw):
     if m > n1:
         GEMM_SUB(A[n1:, n1:], A[n1:, :n1], A[:n1, n1:], **kw)            # src/lu.jl:280
     return A
+
+
+def getrf2(A, ipiv=None, info=None, stream=None, handle: Optional[Handle] = None):
+    """getrf2!(A, ipiv, info) -- src/lu.jl:185-299: recursive LU with partial pivoting of the device matrix A (Float64 / Float32,
+    column-major view), in place and entirely on the device (nla_getrf2).  Returns (A, ipiv, info): `ipiv` a CUDA int64 vector of
+    min(m, n) 1-based pivots, `info` a CUDA int32 scalar tensor (0, or the first i with U[i, i] == 0) -- the call is asynchronous, so
+    read `info.item()` when the value is needed."""
+    import torch
+
+    h = _handle_for(handle, A, stream)
+    pa, rows, cols, lda, dta = _desc(A)
+    k = min(rows, cols)
+    if ipiv is None:
+        ipiv = torch.empty(k, dtype=torch.int64, device=A.device)
+    if info is None:
+        info = torch.zeros((), dtype=torch.int32, device=A.device)
+    if not (ipiv.is_cuda and ipiv.dtype == torch.int64 and ipiv.is_contiguous() and ipiv.numel() >= k):
+        raise NextLAError("ipiv must be a contiguous CUDA int64 vector of at least min(m, n) entries")
+    if not (info.is_cuda and info.dtype == torch.int32 and info.numel() == 1):
+        raise NextLAError("info must be a CUDA int32 scalar")
+    _check(load_library().nla_getrf2(h._h, dta, rows, cols, pa, lda, ipiv.data_ptr(), info.data_ptr(), _stream_ptr(stream, h.device)), h._h)
+    return A, ipiv, info
 
 
 def lauum(uplo: str, A, ib: int = 1024, stream=None, handle: Optional[Handle] = None):

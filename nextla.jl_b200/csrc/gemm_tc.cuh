@@ -66,6 +66,17 @@ template <typename T, int BN> struct TcShape {
   static constexpr int SMEM = STAGES * STAGE + 1024 + (TcCfg<T>::PASSES == 3 ? 16384 : 0);   // + drain staging for Float32
 };
 
+// 3xTF32 operand split.  kind::tf32 reads the top 19 bits of an FP32 word, i.e. it TRUNCATES the 13 low mantissa bits.
+//   hi: the word itself (hi_round = 0: the tensor core's truncation is the split) or rounded to the nearest TF32 (hi_round = 0x1000,
+//       stored masked); lo = a - hi is exact in FP32 either way.
+//   lo has up to 13 significant bits of which the tensor core keeps 11: adding half a TF32 ulp to its bit pattern (lo_round = 0x1000)
+//       turns that truncation into round-to-nearest -- without it every product is short by up to 2^-21 of its size, always in the
+//       same direction, which is the dominant error of a long update chain (recursive LU in Float32: residual 5.9e-5 -> see DESIGN.md 4.4).
+__device__ __forceinline__ void tf32_split(uint32_t v, uint32_t hi_round, uint32_t lo_round, uint32_t& h, uint32_t& l) {
+  h = (v + hi_round) & 0xffffe000u;
+  l = __float_as_uint(__uint_as_float(v) - __uint_as_float(h)) + lo_round;
+}
+
 struct GemmTcParams {
   int M, N, K;
   int a_mn0, a_k0;    // origin of the A operand in its tensor map (operand orientation: mn index, k index)
@@ -74,7 +85,7 @@ struct GemmTcParams {
   long long ldc;
   float beta, sgn, post;
   int overwrite;      // 1: C <- post * sgn * A*B, the old contents of C are not read
-  int raw_hi;         // Float32: 1 = leave the raw FP32 tile in place as the "hi" operand.  kind::tf32 ignores the 13 low mantissa bits
+  int raw_hi;         // Float32 (see tf32_split): 1 = leave the raw FP32 tile in place as the "hi" operand, 0 = hi rounded to nearest and stored, 2 = as 1 with lo truncated too.  kind::tf32 ignores the 13 low mantissa bits
                       // (measured on B200: results bit-identical to explicit masking), so only the lo tile has to be written.
   // K window per tile (batched TRMM, see nla_api.cu): t = tile index along M (or along N when win_on_n; N tile must be 128)
   //   win_mode 0: k in [0, K)                          1: diagonal block, k in [128t, 128t+128) of the V operand, [0,128) of the other
@@ -294,6 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp < DRAIN_WARP0) {
     // ===== Float32 only: split every landed tile into hi (the raw tile, see GemmTcParams::raw_hi) and lo =====
     const int et = threadIdx.x - 64;  // 0..127
+    const uint32_t hi_round = p.raw_hi == 0 ? 0x1000u : 0u, lo_round = p.raw_hi == 2 ? 0u : 0x1000u;
     for (int kt = 0; kt < nk; kt++) {
       const int s = kt % S, it = kt / S;
       mbar_wait_wd(smem_u32(&full_bar[s]), it & 1);
@@ -302,12 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll 4
       for (int i = et; i < HALF_STAGE / 16; i += 128) {
         uint4 v = hi[i], h, l;
-        h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-        l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-        l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-        l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-        l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-        if (!p.raw_hi) hi[i] = h;
+        tf32_split(v.x, hi_round, lo_round, h.x, l.x); tf32_split(v.y, hi_round, lo_round, h.y, l.y);
+        tf32_split(v.z, hi_round, lo_round, h.z, l.z); tf32_split(v.w, hi_round, lo_round, h.w, l.w);
+        if (hi_round) hi[i] = h;
         lo[i] = l;
       }
       fence_proxy_async_smem();

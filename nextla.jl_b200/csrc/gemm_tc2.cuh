@@ -195,6 +195,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   } else if (warp < DRAIN_WARP0) {
     // ===== Float32: write the lo tile of my operands, then arrive on the LEADER's conv barrier =====
     const int et = threadIdx.x - 64;
+    const uint32_t hi_round = p.raw_hi == 0 ? 0x1000u : 0u, lo_round = p.raw_hi == 2 ? 0u : 0x1000u;
     for (int kt = 0; kt < nk; kt++) {
       const int s = kt % S, it = kt / S;
       mbar_wait_wd(smem_u32(&full_bar[s]), it & 1);
@@ -203,12 +204,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll 4
       for (int i = et; i < HALF_STAGE / 16; i += 128) {
         uint4 v = hi[i], h, l;
-        h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-        l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-        l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-        l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-        l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-        if (!p.raw_hi) hi[i] = h;
+        tf32_split(v.x, hi_round, lo_round, h.x, l.x); tf32_split(v.y, hi_round, lo_round, h.y, l.y);
+        tf32_split(v.z, hi_round, lo_round, h.z, l.z); tf32_split(v.w, hi_round, lo_round, h.w, l.w);
+        if (hi_round) hi[i] = h;
         lo[i] = l;
       }
       fence_proxy_async_smem();

@@ -1,0 +1,218 @@
+// getrf.cuh -- the panel factorisation of the reference's recursive LU, `getrf2!` (src/lu.jl:185-299), on the device.
+//
+// The reference recurses on the column count down to single columns (:216-251: pivot search by |re|+|im|, first maximum wins; the
+// interchange; the column scaled by 1/pivot, divided instead when |pivot| < sfmin; a zero pivot recorded in info and the column left
+// alone).  Here the host recursion (nla_api.cu, getrf2_rec) stops at panels of at most GETRF_NB columns, and one COOPERATIVE launch of
+// getrf_panel_kernel factors a whole m x nb panel with the same pivot rule:
+//   * the panel's rows are dealt to the CTAs in contiguous chunks and live in shared memory for the whole launch (one read and one
+//     write of the panel in HBM),
+//   * per column: every CTA finds its own candidate (largest |a|, lowest row on ties) and publishes it WITH that row's nb entries;
+//     the CTA that owns row j also publishes row j; one grid barrier; every CTA then reduces the candidates redundantly, so it knows
+//     the pivot row's contents (= row j of U, needed for its own rank-1 update) and the two owners store the exchanged rows.
+//     The exchange area carries a sequence number in every word (see getrf_ll_words), so there is no barrier object at all: a column
+//     costs one store and two polled reads by the first warp of each CTA.  (Measured per column: 5.2 us with cooperative_groups'
+//     grid.sync() and two block-wide read phases behind it, 7.7 us with a release/acquire counter; the launch stays cooperative for
+//     the co-residency guarantee the polling needs.)  Buffers alternate with the column parity: a CTA can only publish column j + 2
+//     after it has seen every CTA's column j + 1, i.e. after every CTA has finished reading column j.
+//   * ipiv is written relative to the panel's first row (1-based, as the reference's view-relative pivots, :237), info with the
+//     panel's column offset added (:260-262, :289-291) unless an earlier column already set it.
+#pragma once
+#include "common.cuh"
+
+namespace nla {
+
+constexpr int GETRF_NB = 64;        // widest panel
+constexpr int GETRF_THREADS = 256;
+constexpr int GETRF_SLOTS = 8;       // candidate headers polled per lane: up to 256 CTAs
+
+// Exchange area of the panel kernel: every 8-byte word carries 32 bits of payload and the 32-bit sequence number of the column it
+// belongs to, so a reader needs no flag, counter or fence -- it polls the words it wants until they show the right sequence number
+// (8-byte accesses are single-copy atomic).  A double travels as two words.  Per column parity: G headers of 4 words
+// {magnitude lo, magnitude hi, row, unused}, G candidate rows of GETRF_NB doubles, and row j before the interchange.
+constexpr size_t getrf_ll_words(int G) { return 2 * ((size_t)G * 4 + (size_t)G * GETRF_NB * 2 + (size_t)GETRF_NB * 2); }
+
+template <typename T>
+struct GetrfPanelParams {
+  T* A; long long lda;
+  int m, n;                // panel: m rows, n <= GETRF_NB columns
+  int rows_per_cta;
+  long long* ipiv;         // min(m, n) entries
+  int* info;
+  int col_off;             // 0-based global column of the panel's first column
+  unsigned long long* ll;  // exchange area, getrf_ll_words(gridDim.x) words (zeroed once when allocated)
+  unsigned seq_base;       // column j of this launch uses sequence number seq_base + j + 1 (unique across launches on the handle)
+  double sfmin;
+};
+
+__device__ __forceinline__ void ll_put_double(unsigned long long* w, double v, unsigned seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v), s = (unsigned long long)seq << 32;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(w), "l"(s | (b & 0xffffffffull)), "l"(s | (b >> 32)) : "memory");
+}
+__device__ __forceinline__ void ll_peek2(const unsigned long long* w, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(w) : "memory");
+}
+__device__ __forceinline__ void ll_peek3(const unsigned long long* w, unsigned long long& a, unsigned long long& b, unsigned long long& d) {
+  unsigned long long pad;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(w) : "memory");
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(d), "=l"(pad) : "l"(w + 2) : "memory");
+}
+__device__ __forceinline__ void ll_put_int(unsigned long long* w, int v, unsigned seq) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w), "l"(((unsigned long long)seq << 32) | (unsigned)v) : "memory");
+}
+template <typename T>
+__global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfPanelParams<T> p) {
+  extern __shared__ __align__(16) unsigned char getrf_smem[];
+  T* S = reinterpret_cast<T*>(getrf_smem);                 // S[k * rp + i]: column k, local row i
+  __shared__ T prow[GETRF_NB], orow[GETRF_NB];
+  __shared__ double wv[GETRF_THREADS / 32];
+  __shared__ int wi[GETRF_THREADS / 32];
+  __shared__ int s_row;
+  const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rp = p.rows_per_cta;
+  const int r0 = c * rp, nr = min(p.m, r0 + rp) - r0;
+  for (int k = 0; k < p.n; k++)
+    for (int i = tid; i < nr; i += GETRF_THREADS) S[k * rp + i] = p.A[(long long)k * p.lda + r0 + i];
+  __syncthreads();
+  const int steps = min(p.m, p.n);
+  bool have = false; double nbest = -1.0; int nbi = 0x7fffffff;   // candidate carried over from the previous column's update
+  for (int j = 0; j < steps; j++) {
+    const int buf = j & 1;
+    // this CTA's candidate: first row of the largest magnitude among its rows >= j (a NaN counts as the largest)
+    double best = nbest; int bi = nbi;
+    if (!have) {
+      best = -1.0; bi = 0x7fffffff;
+      for (int i = tid; i < nr; i += GETRF_THREADS) {
+        if (r0 + i < j) continue;
+        double v = fabs((double)S[j * rp + i]);
+        if (v != v) v = __longlong_as_double(0x7ff0000000000000ll);
+        if (v > best) { best = v; bi = r0 + i; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { wv[warp] = best; wi[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      // the first warp finishes the CTA's candidate, publishes it with the candidate row's entries, collects everybody's candidates and
+      // fetches the pivot row; the other warps wait at the next __syncthreads
+      best = lane < GETRF_THREADS / 32 ? wv[lane] : -1.0;
+      bi = lane < GETRF_THREADS / 32 ? wi[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      best = __shfl_sync(0xffffffffu, best, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+      const unsigned seq = p.seq_base + (unsigned)j + 1u;
+      unsigned long long* hdr = p.ll + (size_t)buf * ((size_t)G * 4 + (size_t)G * GETRF_NB * 2 + (size_t)GETRF_NB * 2);
+      unsigned long long* rows = hdr + (size_t)G * 4;
+      unsigned long long* rowj = rows + (size_t)G * GETRF_NB * 2;
+      if (lane == 0) ll_put_double(hdr + (size_t)c * 4, best, seq);
+      if (lane == 1) ll_put_int(hdr + (size_t)c * 4 + 2, bi, seq);
+      if (bi != 0x7fffffff)
+        for (int k = lane; k < p.n; k += 32) ll_put_double(rows + ((size_t)c * GETRF_NB + k) * 2, (double)S[k * rp + (bi - r0)], seq);
+      if (j >= r0 && j < r0 + nr)                      // the owner of row j publishes it as it is before the interchange
+        for (int k = lane; k < p.n; k += 32) ll_put_double(rowj + (size_t)k * 2, (double)S[k * rp + (j - r0)], seq);
+      // all of a lane's polls are in flight together: a pass issues every outstanding load, then looks at what came back
+      double v = -1.0; int r = 0x7fffffff;
+      {
+        unsigned pending = 0;
+#pragma unroll
+        for (int sl = 0; sl < GETRF_SLOTS; sl++) if (lane + 32 * sl < G) pending |= 1u << sl;
+        while (pending) {
+          unsigned long long a[GETRF_SLOTS], b[GETRF_SLOTS], d[GETRF_SLOTS];
+#pragma unroll
+          for (int sl = 0; sl < GETRF_SLOTS; sl++)
+            if (pending >> sl & 1) ll_peek3(hdr + (size_t)(lane + 32 * sl) * 4, a[sl], b[sl], d[sl]);
+#pragma unroll
+          for (int sl = 0; sl < GETRF_SLOTS; sl++)
+            if ((pending >> sl & 1) && (unsigned)(a[sl] >> 32) == seq && (unsigned)(b[sl] >> 32) == seq && (unsigned)(d[sl] >> 32) == seq) {
+              const double gv = __longlong_as_double((long long)((a[sl] & 0xffffffffull) | (b[sl] << 32)));
+              const int gr = (int)(unsigned)d[sl];
+              if (gv > v || (gv == v && gr < r)) { v = gv; r = gr; }
+              pending &= ~(1u << sl);
+            }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
+        if (ov > v || (ov == v && orr < r)) { v = ov; r = orr; }
+      }
+      const bool mine = r >= r0 && r < r0 + nr && r != j;     // this CTA stores the old row j at the pivot's position
+      {
+        const unsigned long long* wrow = rows + (size_t)(r / rp) * GETRF_NB * 2;
+        unsigned pending = 0;    // bits 0,1: pivot row entries lane, lane + 32; bits 2,3: the same entries of row j
+        if (lane < p.n) pending |= mine ? 5u : 1u;
+        if (lane + 32 < p.n) pending |= mine ? 10u : 2u;
+        while (pending) {
+          unsigned long long a[4], b[4];
+#pragma unroll
+          for (int sl = 0; sl < 4; sl++)
+            if (pending >> sl & 1) ll_peek2((sl < 2 ? wrow : rowj) + (size_t)(lane + 32 * (sl & 1)) * 2, a[sl], b[sl]);
+#pragma unroll
+          for (int sl = 0; sl < 4; sl++)
+            if ((pending >> sl & 1) && (unsigned)(a[sl] >> 32) == seq && (unsigned)(b[sl] >> 32) == seq) {
+              const T x = (T)__longlong_as_double((long long)((a[sl] & 0xffffffffull) | (b[sl] << 32)));
+              (sl < 2 ? prow : orow)[lane + 32 * (sl & 1)] = x;
+              pending &= ~(1u << sl);
+            }
+        }
+      }
+      if (lane == 0) s_row = r;
+    }
+    __syncthreads();
+    const int pr = s_row;
+    const T piv = prow[j];
+    if (c == 0 && tid == 0) {
+      p.ipiv[j] = (long long)pr + 1;
+      if (piv == T(0) && *p.info == 0) *p.info = p.col_off + j + 1;
+    }
+    if (pr != j && tid < p.n) {
+      if (j >= r0 && j < r0 + nr) S[tid * rp + (j - r0)] = prow[tid];
+      if (pr >= r0 && pr < r0 + nr) S[tid * rp + (pr - r0)] = orow[tid];
+    }
+    __syncthreads();
+    // scale column j, rank-1 update of the columns to its right; the thread's candidate for column j + 1 falls out of the update
+    have = (piv != T(0)) && (j + 1 < p.n);
+    nbest = -1.0; nbi = 0x7fffffff;
+    if (piv != T(0)) {
+      const bool mul = fabs((double)piv) >= p.sfmin;
+      const T inv = T(1) / piv;
+      for (int i = tid; i < nr; i += GETRF_THREADS) {
+        if (r0 + i <= j) continue;
+        T l = S[j * rp + i];
+        l = mul ? l * inv : l / piv;
+        S[j * rp + i] = l;
+        if (j + 1 < p.n) {
+          const T x = S[(j + 1) * rp + i] - l * prow[j + 1];
+          S[(j + 1) * rp + i] = x;
+          double v = fabs((double)x);
+          if (v != v) v = __longlong_as_double(0x7ff0000000000000ll);
+          if (v > nbest) { nbest = v; nbi = r0 + i; }
+        }
+#pragma unroll 8
+        for (int k = j + 2; k < p.n; k++) S[k * rp + i] -= l * prow[k];
+      }
+    }
+    // no barrier here: the next column's __syncthreads orders these writes before the first warp reads S, and prow / orow / wv / wi are
+    // rewritten only behind it
+  }
+  __syncthreads();
+  for (int k = 0; k < p.n; k++)
+    for (int i = tid; i < nr; i += GETRF_THREADS) p.A[(long long)k * p.lda + r0 + i] = S[k * rp + i];
+}
+
+// ipiv[i] += shift for i < count: the reference's pivot adjustment after the second recursive call (src/lu.jl:293-295)
+__global__ void __launch_bounds__(256) ipiv_shift_kernel(long long* __restrict__ ipiv, long long count, long long shift) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) ipiv[i] += shift;
+}
+
+}  // namespace nla

@@ -27,6 +27,7 @@
 #include "laswp.cuh"
 #include "probe.cuh"
 #include "complex.cuh"
+#include "getrf.cuh"
 
 using namespace nla;
 
@@ -102,6 +103,9 @@ struct nla_context {
   int64_t nvtx;         // 1 = NVTX ranges around calls and schedule ops
   void* lauum_ws; size_t lauum_ws_bytes;   // one masked diagonal block (nla_lauum)
   void* cplx_ws; size_t cplx_ws_bytes;     // planar copies of A and B of a complex call (complex.cuh)
+  void* getrf_ws;       // candidate exchange of the LU panel kernel (getrf.cuh); fixed size, allocated on first use
+  uint32_t getrf_seq;   // sequence numbers handed out to panel columns so far
+  void* laswp_ws; size_t laswp_ws_bytes;   // interchange plan of nla_laswp / nla_getrf2 (laswp.cuh)
 };
 
 static const uint32_t NLA_MAGIC = 0x4e4c4142u;  // "NLAB"
@@ -1450,7 +1454,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
   ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->gated_macro = 2048; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
-  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
+  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0; ctx->getrf_ws = nullptr; ctx->getrf_seq = 0; ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1485,6 +1489,8 @@ int nla_destroy(nla_handle_t h) {
   if (h->stream_dev) { if (h->stream_dev_async) cudaFreeAsync(h->stream_dev, 0); else cudaFree(h->stream_dev); }
   if (h->stream_flags_host) cudaFreeHost(h->stream_flags_host);
   if (h->cplx_ws) cudaFreeAsync(h->cplx_ws, 0);
+  if (h->getrf_ws) cudaFree(h->getrf_ws);
+  if (h->laswp_ws) cudaFreeAsync(h->laswp_ws, 0);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
   for (auto e : h->panel_prep_events) cudaEventDestroy(e);
@@ -1511,7 +1517,7 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "host_macro_mid")) { if (value < 128 || (value & (value - 1))) return NLA_ERR_INVALID_DIM; h->host_macro_mid = value; return NLA_OK; }
   if (!strcmp(key, "tc_bn")) { if (value != 0 && value != 128 && value != 256) return NLA_ERR_INVALID_DIM; h->tc_bn = value; return NLA_OK; }
   if (!strcmp(key, "tc_cg")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tc_cg = value; return NLA_OK; }
-  if (!strcmp(key, "tf32_raw_hi")) { h->tf32_raw_hi = value != 0; return NLA_OK; }
+  if (!strcmp(key, "tf32_raw_hi")) { if (value < 0 || value > 2) return NLA_ERR_INVALID_DIM; h->tf32_raw_hi = value; return NLA_OK; }
   if (!strcmp(key, "trmm_batched")) { h->trmm_batched = value != 0; return NLA_OK; }
   if (!strcmp(key, "pdl")) { h->pdl = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_dup")) { h->inv_dup = value != 0; return NLA_OK; }
@@ -1882,7 +1888,7 @@ static int lauum_typed(nla_context* ctx, bool lower, int64_t n, T* A, int64_t ld
     const size_t need = (size_t)ldw * ib * es;
     if (ctx->lauum_ws_bytes < need) {
       if (ctx->lauum_ws) NLA_CUDA(ctx, cudaFreeAsync(ctx->lauum_ws, st));
-      ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0;
+      ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0;
       NLA_CUDA(ctx, cudaMallocAsync(&ctx->lauum_ws, need, st));
       ctx->lauum_ws_bytes = need; ctx->ws_allocs++;
     }
@@ -1971,6 +1977,119 @@ extern "C" int nla_lauum(nla_handle_t h, char uplo, int dtype, int64_t n, void* 
     case NLA_F32: return lauum_typed<float>(h, uplo == 'L', n, (float*)A, lda, ib, st);
     default: return lauum_typed<__half>(h, uplo == 'L', n, (__half*)A, lda, ib, st);
   }
+}
+
+template <typename T>
+static int launch_laswp_fwd(nla_context* ctx, T* A, int64_t lda, int64_t ncols, int64_t k1, int64_t k2, const long long* ipiv, cudaStream_t st) {
+  const int64_t steps = k2 - k1 + 1;
+  if (steps <= 0 || ncols <= 0) return NLA_OK;
+  const int64_t padded = (steps + LASWP_NB - 1) / LASWP_NB * LASWP_NB;
+  const size_t need = 3 * (size_t)padded * sizeof(int);
+  if (ctx->laswp_ws_bytes < need) {
+    if (ctx->laswp_ws) NLA_CUDA(ctx, cudaFreeAsync(ctx->laswp_ws, st));
+    ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
+    const size_t bytes = std::max<size_t>(need, 3 * 16384 * sizeof(int));
+    NLA_CUDA(ctx, cudaMallocAsync(&ctx->laswp_ws, bytes, st));
+    ctx->laswp_ws_bytes = bytes; ctx->ws_allocs++;
+  }
+  int* plan_t = (int*)ctx->laswp_ws; int* plan_row = plan_t + padded; int* plan_tgt = plan_row + padded;
+  const int64_t nbatches = padded / LASWP_NB;
+  laswp_plan_kernel<<<(unsigned)((nbatches + 127) / 128), 128, 0, st>>>(ipiv, k1, k2, plan_t, plan_row, plan_tgt);
+  const int64_t cols_per_cta = 2 * (LASWP_THREADS / 32);
+  laswp_apply_kernel<T><<<(unsigned)((ncols + cols_per_cta - 1) / cols_per_cta), LASWP_THREADS, 0, st>>>(A, lda, ncols, k1, k2, plan_t, plan_row, plan_tgt);
+  ctx->launches += 2;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+// ---- recursive LU (getrf.cuh) ----------------------------------------------------------------------------------
+// getrf2!(A, ipiv, info) of the reference (src/lu.jl:185-299) with every step on the device: the recursion below splits the columns like
+// the reference (n1 = min(m, n) / 2, rounded down to a multiple of 32 once it is that large so that the sub-blocks keep the alignment
+// the TMA kernels want -- the factorisation does not depend on where the columns are split), factors the left part, applies its
+// interchanges to the right part (laswp, :274), solves with the unit-lower block (the recursive TRSM of this library, :277), updates A22
+// (:280), factors A22, shifts its pivots (:293-295) and applies them to the left part (:298).  Panels of <= GETRF_NB columns go to the
+// cooperative panel kernel.
+template <typename T>
+static int getrf_panel(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda, long long* ipiv, int* info, int64_t col_off, cudaStream_t st) {
+  const int G_max = std::min(ctx->sm_count, 32 * GETRF_SLOTS);
+  const size_t smem_cap = 200 * 1024;
+  static const int64_t min_rows = [] { const char* e = getenv("NLA_GETRF_ROWS"); return e ? std::max<int64_t>(32, atoll(e)) : 64; }();   // probe hook
+  int64_t rows = std::max<int64_t>(min_rows, (m + G_max - 1) / G_max);
+  while (rows > (m + G_max - 1) / G_max && (size_t)rows * n * sizeof(T) > smem_cap) rows /= 2;
+  if ((size_t)rows * n * sizeof(T) > smem_cap) return NLA_ERR_UNSUPPORTED;   // the caller narrows the panel
+  const int G = (int)((m + rows - 1) / rows);
+  if (!ctx->getrf_ws) {
+    const size_t bytes = getrf_ll_words(G_max) * sizeof(unsigned long long);
+    NLA_CUDA(ctx, cudaMalloc(&ctx->getrf_ws, bytes));
+    NLA_CUDA(ctx, cudaMemsetAsync(ctx->getrf_ws, 0, bytes, st));
+    ctx->ws_allocs++;
+    ctx->getrf_seq = 0;
+  }
+  GetrfPanelParams<T> p;
+  p.A = A; p.lda = lda; p.m = (int)m; p.n = (int)n; p.rows_per_cta = (int)rows; p.ipiv = ipiv; p.info = info; p.col_off = (int)col_off;
+  p.ll = (unsigned long long*)ctx->getrf_ws;
+  p.seq_base = ctx->getrf_seq;
+  ctx->getrf_seq += (uint32_t)std::min(m, n);
+  if (ctx->getrf_seq > 0xfff00000u) {   // wrap: start over on a clean exchange area (stream-ordered behind the launches so far)
+    NLA_CUDA(ctx, cudaMemsetAsync(ctx->getrf_ws, 0, getrf_ll_words(G_max) * sizeof(unsigned long long), st));
+    p.seq_base = 0; ctx->getrf_seq = (uint32_t)std::min(m, n);
+  }
+  p.sfmin = std::is_same<T, double>::value ? 2.2250738585072014e-308 : 1.17549435e-38;   // lamch('S')
+  const size_t smem = (size_t)rows * n * sizeof(T);
+  { int arc = ensure_smem_attr(ctx, getrf_panel_kernel<T>, (int)smem_cap); if (arc != NLA_OK) return arc; }
+  void* args[] = {(void*)&p};
+  NLA_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)getrf_panel_kernel<T>, dim3((unsigned)G), dim3(GETRF_THREADS), args, smem, st));
+  ctx->launches++;
+  return NLA_OK;
+}
+
+template <typename T>
+static int getrf2_rec(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda, long long* ipiv, int* info, int64_t col_off, int64_t nb,
+                      cudaStream_t st) {
+  const int dtype = std::is_same<T, double>::value ? NLA_F64 : NLA_F32;
+  if (m == 1) return getrf_panel<T>(ctx, 1, 1, A, lda, ipiv, info, col_off, st);     // :216-222: ipiv[1] = 1, zero check, nothing else
+  if (n <= nb) return getrf_panel<T>(ctx, m, n, A, lda, ipiv, info, col_off, st);
+  const int64_t mn = std::min(m, n);
+  int64_t n1 = mn / 2;
+  if (n1 >= 32) n1 &= ~31ll;
+  const int64_t n2 = n - n1;
+  int rc = getrf2_rec<T>(ctx, m, n1, A, lda, ipiv, info, col_off, nb, st);
+  if (rc != NLA_OK) return rc;
+  T* A12 = A + n1 * lda;
+  if ((rc = launch_laswp_fwd<T>(ctx, A12, lda, n2, 1, n1, ipiv, st)) != NLA_OK) return rc;
+  Problem P;
+  if ((rc = make_problem(P, 'L', 'L', 'N', 'S', dtype, n1, n2, 1.0, A, lda, A12, lda, 'U')) != NLA_OK) return rc;
+  if ((rc = dispatch(ctx, P, st)) != NLA_OK) return rc;
+  T* A22 = A12 + n1;
+  if ((rc = gemm_update_typed<T>(ctx, 'N', 'N', m - n1, n2, n1, -1, A + n1, lda, A12, lda, A22, lda, st)) != NLA_OK) return rc;
+  if ((rc = getrf2_rec<T>(ctx, m - n1, n2, A22, lda, ipiv + n1, info, col_off + n1, nb, st)) != NLA_OK) return rc;
+  ipiv_shift_kernel<<<(unsigned)((mn - n1 + 255) / 256), 256, 0, st>>>(ipiv + n1, mn - n1, n1);
+  ctx->launches++;
+  if ((rc = launch_laswp_fwd<T>(ctx, A, lda, n1, n1 + 1, mn, ipiv, st)) != NLA_OK) return rc;
+  NLA_CUDA(ctx, cudaGetLastError());
+  return NLA_OK;
+}
+
+extern "C" int nla_getrf2(nla_handle_t h, int dtype, int64_t m, int64_t n, void* A, int64_t lda, int64_t* ipiv, int* info, void* stream) {
+  if (!valid(h)) return NLA_ERR_INVALID_HANDLE;
+  if (dtype != NLA_F64 && dtype != NLA_F32) return dtype == NLA_F16 || dtype == NLA_C64 || dtype == NLA_C128 ? NLA_ERR_UNSUPPORTED : NLA_ERR_INVALID_DTYPE;
+  if (m < 0 || n < 0 || m >= (1ll << 31) || n >= (1ll << 31) || lda < std::max<int64_t>(1, m)) return NLA_ERR_INVALID_DIM;   // :192-203
+  if (!info) return NLA_ERR_NULL_POINTER;
+  NLA_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  NLA_CUDA(h, cudaMemsetAsync(info, 0, sizeof(int), st));                          // :190
+  if (m == 0 || n == 0) return NLA_OK;                                             // :206
+  if (!A || !ipiv) return NLA_ERR_NULL_POINTER;
+  NvtxRange call_range(h, "nla_getrf2 m=%lld n=%lld dtype=%lld", (long long)m, (long long)n, (long long)dtype);
+  // widest panel whose row chunk fits one CTA's shared memory
+  const size_t es = dtype_size(dtype);
+  const int64_t gmax = std::min(h->sm_count, 32 * GETRF_SLOTS);
+  const int64_t rows = std::max<int64_t>(64, (m + gmax - 1) / gmax);
+  int64_t nb = GETRF_NB;
+  while (nb > 1 && (size_t)rows * nb * es > 200 * 1024) nb /= 2;
+  if ((size_t)rows * nb * es > 200 * 1024) return NLA_ERR_UNSUPPORTED;
+  return dtype == NLA_F64 ? getrf2_rec<double>(h, m, n, (double*)A, lda, (long long*)ipiv, info, 0, nb, st)
+                          : getrf2_rec<float>(h, m, n, (float*)A, lda, (long long*)ipiv, info, 0, nb, st);
 }
 
 // ---- complex element types (complex.cuh) ----------------------------------------------------------------------
@@ -2505,13 +2624,21 @@ int nla_laswp(nla_handle_t h, int dtype, int64_t rows, int64_t ncols, void* A, i
   if (k1 < 1 || k2 > rows) return NLA_ERR_INVALID_DIM;
   if (!A || !ipiv) return NLA_ERR_NULL_POINTER;
   NLA_ON_DEVICE(h);
-  const unsigned grid = (unsigned)((ncols + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   const long long* piv = (const long long*)ipiv;
-  switch (dtype) {
-    case NLA_F64: laswp_kernel<double><<<grid, 256, 0, st>>>((double*)A, lda, ncols, k1, k2, piv, incx < 0); break;
-    case NLA_F32: laswp_kernel<float><<<grid, 256, 0, st>>>((float*)A, lda, ncols, k1, k2, piv, incx < 0); break;
-    default: laswp_kernel<__half><<<grid, 256, 0, st>>>((__half*)A, lda, ncols, k1, k2, piv, incx < 0); break;
+  if (incx > 0) {
+    switch (dtype) {
+      case NLA_F64: return launch_laswp_fwd<double>(h, (double*)A, lda, ncols, k1, k2, piv, st);
+      case NLA_F32: return launch_laswp_fwd<float>(h, (float*)A, lda, ncols, k1, k2, piv, st);
+      default: return launch_laswp_fwd<__half>(h, (__half*)A, lda, ncols, k1, k2, piv, st);
+    }
+  } else {
+    const unsigned grid = (unsigned)((ncols + 255) / 256);
+    switch (dtype) {
+      case NLA_F64: laswp_kernel<double><<<grid, 256, 0, st>>>((double*)A, lda, ncols, k1, k2, piv, 1); break;
+      case NLA_F32: laswp_kernel<float><<<grid, 256, 0, st>>>((float*)A, lda, ncols, k1, k2, piv, 1); break;
+      default: laswp_kernel<__half><<<grid, 256, 0, st>>>((__half*)A, lda, ncols, k1, k2, piv, 1); break;
+    }
   }
   h->launches++;
   NLA_CUDA(h, cudaGetLastError());

@@ -175,6 +175,23 @@ function panel_order(side::Char, uplo::Char, transpose::Char, func::Char, n::Int
 end
 
 """
+    getrf2!(A::StridedCuMatrix{T}, ipiv::CuVector{Int64}, info)
+
+The reference's recursive LU (src/lu.jl:185) on a device matrix: A = P*L*U in place, `ipiv` the 1-based row interchanges (device vector
+of at least min(m, n) entries).  Returns `(A, ipiv, info)` like the reference, `info` read back from the device after the call (the one
+synchronisation: the reference's return value is a host integer): 0, or the first i with U[i, i] == 0.
+"""
+function NextLA.getrf2!(A::StridedCuMatrix{T}, ipiv::CuVector{Int64}, info::Integer=0) where {T<:Union{Float32,Float64}}
+    m, n = size(A)
+    length(ipiv) >= min(m, n) || throw(DimensionMismatch("ipiv has $(length(ipiv)) entries, min(m, n) = $(min(m, n))"))
+    dinfo = CUDA.zeros(Cint, 1)
+    GC.@preserve A ipiv dinfo check(ccall((:nla_getrf2, libnextla), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, CuPtr{Cvoid}, Int64, CuPtr{Int64}, CuPtr{Cint}, Ptr{Cvoid}),
+        handle(), dtype_code(T), m, n, pointer(A), max(1, stride(A, 2)), pointer(ipiv), pointer(dinfo), CUDA.stream().handle))
+    return A, ipiv, Int(Array(dinfo)[1])
+end
+
+"""
     lauum!(uplo, n, A::StridedCuMatrix{T}, ib)
 
 Same signature as the reference (src/lauum.jl:52): A := U*U^H (uplo 'U') or L^H*L (uplo 'L') in the `uplo` triangle of the device matrix.

@@ -52,4 +52,15 @@ for dtype, tol in ((np.float16, 1e-2), (np.float32, 1e-5)):
         assert fb == 2, (dtype, side, uplo, fb)
         assert rp.error_metric(side, uplo, "N", 1.0, "S", A, B0, nla.to_numpy(dB)) < tol
 h.set_option("inv_guard_kappa", 0)
+# recursive LU: cooperative panel kernel (cross-CTA polling), planned laswp, unit-lower solves, updates
+from scipy.linalg import lu_factor
+for dtype, m, n in ((np.float64, 700, 520), (np.float32, 300, 420)) if not QUICK else ((np.float64, 330, 200),):
+    A0 = (rng.rand(m, n) - 0.5).astype(dtype)
+    dA = nla.colmajor(A0)
+    _, ipiv, info = nla.getrf2(dA); torch.cuda.synchronize()
+    lu_ref, piv_ref = lu_factor(A0.astype(np.float64), check_finite=False)
+    assert int(info.item()) == 0
+    if dtype == np.float64:
+        assert np.array_equal(ipiv.cpu().numpy() - 1, piv_ref[:min(m, n)])
+        assert np.linalg.norm(nla.to_numpy(dA) - lu_ref) / np.linalg.norm(lu_ref) < 1e-11
 print("sanitize_small ok, worst err/tol", worst)

@@ -1,0 +1,166 @@
+"""nla_getrf2 -- the reference's recursive LU (getrf2!, src/lu.jl:185-299) entirely on the device.
+
+Checked against LAPACK getrf (SciPy): P*A = L*U against the original matrix, the pivot sequence (partial pivoting with "first largest
+magnitude" is unique for random data in Float64), info for exactly singular input, the reference's own test grid
+(test/lu.jl:70-71: m in 10/100/1000, n in m, 0.9 m, 1.1 m, criterion L*U ~ A[p, :])."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def apply_pivots(A0, piv):
+    PA = A0.copy()
+    for i, p in enumerate(piv):
+        if p != i:
+            PA[[i, p]] = PA[[p, i]]
+    return PA
+
+
+def factor(nla, A0):
+    import torch
+
+    dA = nla.colmajor(A0)
+    _, ipiv, info = nla.getrf2(dA)
+    torch.cuda.synchronize()
+    return nla.to_numpy(dA), ipiv.cpu().numpy() - 1, int(info.item())
+
+
+def check_lu(A0, LU, piv, tol):
+    m, n = A0.shape
+    k = min(m, n)
+    assert piv.shape == (k,)
+    assert np.all(piv >= np.arange(k)) and np.all(piv < m)
+    L = np.tril(LU[:, :k], -1).astype(np.float64) + np.eye(m, k)
+    U = np.triu(LU[:k, :]).astype(np.float64)
+    assert np.all(np.abs(np.tril(LU[:, :k], -1)) <= 1.0 + 1e-6)     # partial pivoting: multipliers bounded by one
+    PA = apply_pivots(A0.astype(np.float64), piv)
+    assert np.linalg.norm(PA - L @ U) / np.linalg.norm(A0) < tol
+
+
+SHAPES = [(1, 1), (1, 7), (7, 1), (2, 2), (33, 33), (64, 40), (40, 64), (257, 300), (300, 257), (1024, 1024), (1500, 900), (700, 1100), (3000, 3000)]
+
+
+@pytest.mark.parametrize("m,n", SHAPES)
+def test_getrf2_fp64_matches_lapack(nla, gpu, m, n):
+    from scipy.linalg import lu_factor
+
+    rng = np.random.RandomState(1000 * m + n)
+    A0 = rng.rand(m, n) - 0.5
+    LU, piv, info = factor(nla, A0)
+    assert info == 0
+    check_lu(A0, LU, piv, 1e-13)
+    lu_ref, piv_ref = lu_factor(A0, check_finite=False)
+    assert np.array_equal(piv, piv_ref[:min(m, n)])
+    assert np.linalg.norm(LU - lu_ref) / np.linalg.norm(lu_ref) < 1e-10
+
+
+@pytest.mark.parametrize("m,n", SHAPES)
+def test_getrf2_fp32(nla, gpu, m, n):
+    rng = np.random.RandomState(7 * m + n)
+    A0 = (rng.rand(m, n) - 0.5).astype(np.float32)
+    LU, piv, info = factor(nla, A0)
+    assert info == 0
+    # the Float32 updates run as 3xTF32 on the tensor cores, whose accumulation truncates: measured 5.4e-5 at n = 3000
+    # where LAPACK's sgetrf has 7.8e-6 and the FMA kernels (option force_simt) 7.2e-6; the reference's own criterion is sqrt(eps) = 3.4e-4
+    check_lu(A0, LU, piv, 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_getrf2_reference_grid(nla, gpu, dtype):
+    """test/lu.jl:68-91 (default RowMaximum pivoting): m in 10/100/1000, n in m, 0.9 m, 1.1 m; L*U ~ A[p, :] (isapprox: rtol sqrt(eps))."""
+    for m in (10, 100, 1000):
+        for n in (m, m // 10 * 9, m // 10 * 11):
+            rng = np.random.RandomState(m * 3 + n)
+            A0 = rng.rand(m, n).astype(dtype)
+            LU, piv, info = factor(nla, A0)
+            assert info == 0
+            k = min(m, n)
+            L = np.tril(LU[:, :k], -1).astype(np.float64) + np.eye(m, k)
+            U = np.triu(LU[:k, :]).astype(np.float64)
+            PA = apply_pivots(A0.astype(np.float64), piv)
+            assert np.linalg.norm(L @ U - PA) <= np.sqrt(np.finfo(dtype).eps) * max(np.linalg.norm(L @ U), np.linalg.norm(PA))
+
+
+def test_getrf2_fp32_fma_kernels_reach_lapack_accuracy(nla, gpu):
+    """Option force_simt keeps the Float32 updates on the FMA kernels: the residual is then LAPACK's (sgetrf: 7.8e-6 on this matrix)."""
+    m = n = 3000
+    rng = np.random.RandomState(7 * m + n)
+    A0 = (rng.rand(m, n) - 0.5).astype(np.float32)
+    gpu.set_option("force_simt", 1)
+    try:
+        LU, piv, info = factor(nla, A0)
+    finally:
+        gpu.set_option("force_simt", 0)
+    assert info == 0
+    check_lu(A0, LU, piv, 1.2e-5)
+
+
+def test_getrf2_padded_leading_dimension_and_views(nla, gpu):
+    """lda > m and a sub-matrix view of a larger device matrix; the rows/columns outside the view are untouched."""
+    import torch
+    from scipy.linalg import lu_factor
+
+    rng = np.random.RandomState(5)
+    big = rng.rand(900, 800) - 0.5
+    dbig = nla.colmajor(big)
+    view = dbig[100:700, 64:564]                       # 600 x 500, lda = 900
+    _, ipiv, info = nla.getrf2(view)
+    torch.cuda.synchronize()
+    out = nla.to_numpy(dbig)
+    lu_ref, piv_ref = lu_factor(big[100:700, 64:564], check_finite=False)
+    assert int(info.item()) == 0
+    assert np.array_equal(ipiv.cpu().numpy() - 1, piv_ref)
+    assert np.linalg.norm(out[100:700, 64:564] - lu_ref) / np.linalg.norm(lu_ref) < 1e-10
+    mask = np.ones_like(big, dtype=bool)
+    mask[100:700, 64:564] = False
+    assert np.array_equal(out[mask], big[mask])
+
+
+@pytest.mark.parametrize("n,zero_col", [(100, 5), (100, 0), (640, 300), (64, 63)])
+def test_getrf2_reports_the_first_zero_pivot(nla, gpu, n, zero_col):
+    """src/lu.jl:246-249 / :260-262 / :289-291: an exactly zero pivot is reported as info = its (1-based) column; the factorisation
+    completes.  LAPACK's getrf gives the same info."""
+    from scipy.linalg import lapack
+
+    rng = np.random.RandomState(n + zero_col)
+    A0 = rng.rand(n, n) - 0.5
+    A0[:, zero_col] = 0.0
+    if zero_col + 7 < n:
+        A0[:, zero_col + 7] = 0.0                      # a later zero column must not overwrite the first
+    LU, piv, info = factor(nla, A0)
+    lu_ref, piv_ref, info_ref = lapack.dgetrf(A0)
+    assert info == info_ref == zero_col + 1
+    assert np.array_equal(piv, piv_ref)
+    assert np.linalg.norm(LU - lu_ref) / np.linalg.norm(lu_ref) < 1e-10
+
+
+def test_getrf2_tiny_pivot_is_divided_not_scaled(nla, gpu):
+    """src/lu.jl:239-243: a pivot below sfmin divides the column (its reciprocal would overflow)."""
+    A0 = np.array([[1e-310, 2.0, 1.0], [5e-311, 1.0, 3.0], [2e-311, 4.0, 2.0]])
+    LU, piv, info = factor(nla, A0)
+    assert info == 0 and list(piv) == [0, 2, 2]
+    assert np.all(np.isfinite(LU))
+    # multipliers 2e-311 / 1e-310 and 5e-311 / 1e-310 (1 / 1e-310 overflows); the second step then takes 4 - 0.2 * 2 = 3.6 as its pivot.
+    # (OpenBLAS's getrf leaves such a column unscaled, so LAPACK is no oracle here; the reference's rule is src/lu.jl:239-243.)
+    want = np.array([[1e-310, 2.0, 1.0], [0.2, 3.6, 1.8], [0.5, 0.0, 2.5]])
+    assert np.allclose(LU, want, rtol=1e-3, atol=1e-12)
+
+
+def test_getrf2_argument_checks(nla, gpu):
+    import ctypes
+    import torch
+
+    lib = nla.load_library()
+    h = gpu
+    A = torch.zeros(16, dtype=torch.float64, device="cuda")
+    ipiv = torch.zeros(4, dtype=torch.int64, device="cuda")
+    info = torch.full((), 7, dtype=torch.int32, device="cuda")
+    call = lambda dt, m, n, lda, a=A.data_ptr(), p=ipiv.data_ptr(), i=info.data_ptr(): lib.nla_getrf2(h._h, dt, m, n, a, lda, p, i, None)
+    assert call(0, -1, 4, 4) == 2 and call(0, 4, -1, 4) == 2 and call(0, 4, 4, 3) == 2       # src/lu.jl:192-203
+    assert call(2, 4, 4, 4) == 7 and call(3, 4, 4, 4) == 7 and call(9, 4, 4, 4) == 3           # Float16 / complex unsupported, bad dtype
+    assert call(0, 4, 4, 4, i=None) == 4 and call(0, 4, 4, 4, a=None) == 4
+    assert lib.nla_getrf2(None, 0, 4, 4, A.data_ptr(), 4, ipiv.data_ptr(), info.data_ptr(), None) == 8
+    assert call(0, 0, 4, 1) == 0                                                               # quick return (:206) with info cleared
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0

@@ -172,7 +172,8 @@ int nla_lauum(nla_handle_t handle, char uplo, int dtype, int64_t n, void *A, int
 
 /* Diagonal-block leaves: LeftLowerTRSM!/LeftUpperTRSM!/RightLowerTRSM!/RightUpperTRSM!  -- src/trsm.jl:128-150
  * and LeftLowerTRMM!/.../RightUpperTRMM!                                               -- src/trmm.jl:332-389.
- * One launch of the leaf kernel, no recursion: n <= nla_leaf_max(dtype).  (The reference caps at 1024 / 16.) */
+ * n <= nla_leaf_max(dtype) = 1024, the reference's cap (its kernels hold the block in 1024-entry shared arrays, src/trsm.jl:9-11):
+ * one launch of the leaf kernel up to n = 128, the library's blocked path (fused slab / block inverses) above. */
 int nla_trsm_leaf(nla_handle_t handle, char side, char uplo, int dtype, int64_t n, int64_t m,
                   const void *A, int64_t lda, void *B, int64_t ldb, void *stream);
 int nla_trmm_leaf(nla_handle_t handle, char side, char uplo, int dtype, int64_t n, int64_t m,

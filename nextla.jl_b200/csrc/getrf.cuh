@@ -23,6 +23,7 @@ namespace nla {
 
 constexpr int GETRF_NB = 64;        // widest panel
 constexpr int GETRF_THREADS = 256;
+constexpr int GETRF_UG = 16;         // columns per register group of the rank-1 update
 constexpr int GETRF_SLOTS = 8;       // candidate headers polled per lane: up to 256 CTAs
 
 // Exchange area of the panel kernel: every 8-byte word carries 32 bits of payload and the 32-bit sequence number of the column it
@@ -59,6 +60,55 @@ __device__ __forceinline__ void ll_peek3(const unsigned long long* w, unsigned l
 __device__ __forceinline__ void ll_put_int(unsigned long long* w, int v, unsigned seq) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(w), "l"(((unsigned long long)seq << 32) | (unsigned)v) : "memory");
 }
+// Warp-wide "largest magnitude, lowest row on ties" on (best, bi) pairs; best >= 0 (or -1 with bi = INT_MAX for "no candidate").  The bit
+// pattern of a non-negative double orders like an unsigned integer, so three redux.sync instructions (high word, low word among the
+// lanes that match the high word, lowest row among the lanes that match both) replace five rounds of 64-bit shuffles and FP64 compares
+// (measured with clock64 stamps: ~100 cycles per shuffle round, three such reductions per column).  Every lane gets the result.
+__device__ __forceinline__ void getrf_warp_argmax(double& best, int& bi) {
+  const unsigned long long key = bi == 0x7fffffff ? 0ull : (unsigned long long)__double_as_longlong(best);
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  const unsigned mi = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)bi : 0x7fffffffu);
+  bi = (int)mi;
+  best = mi == 0x7fffffffu ? -1.0 : __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+
+// Row i of the rank-1 update of step j: l = a_ij / pivot, a_ik -= l * u_jk for k > j; returns |a_i,j+1| after the update (the row's
+// candidate for the next column; -1 when there is none).  The columns are taken in groups of GETRF_UG with all loads of a group ahead of its
+// stores: S and the pivot row are both in shared memory, and with one load - FMA - store per column the compiler must keep every load
+// behind the previous store (possible alias), which made a column cost ~60 cycles of latency each -- 2 us per step whatever the row count.
+template <typename T>
+__device__ __forceinline__ double getrf_update_row(T* __restrict__ Si, int rp, int j, int n, bool mul, T inv, T piv, const T* __restrict__ prow) {
+  T l = Si[j * rp];
+  l = mul ? l * inv : l / piv;
+  Si[j * rp] = l;
+  double next = -1.0;
+  int k = j + 1;
+  if (k < n) {
+    T x[GETRF_UG];
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) x[u] = (k + u < n) ? Si[(k + u) * rp] : T(0);
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) x[u] -= l * ((k + u < n) ? prow[k + u] : T(0));
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) if (k + u < n) Si[(k + u) * rp] = x[u];
+    next = fabs((double)x[0]);
+    if (next != next) next = __longlong_as_double(0x7ff0000000000000ll);
+    k += GETRF_UG;
+  }
+  for (; k < n; k += GETRF_UG) {
+    T x[GETRF_UG];
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) x[u] = (k + u < n) ? Si[(k + u) * rp] : T(0);
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) x[u] -= l * ((k + u < n) ? prow[k + u] : T(0));
+#pragma unroll
+    for (int u = 0; u < GETRF_UG; u++) if (k + u < n) Si[(k + u) * rp] = x[u];
+  }
+  return next;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfPanelParams<T> p) {
   extern __shared__ __align__(16) unsigned char getrf_smem[];
@@ -88,12 +138,7 @@ __global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfP
         if (v > best) { best = v; bi = r0 + i; }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
+    getrf_warp_argmax(best, bi);
     if (lane == 0) { wv[warp] = best; wi[warp] = bi; }
     __syncthreads();
     if (warp == 0) {
@@ -101,12 +146,7 @@ __global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfP
       // fetches the pivot row; the other warps wait at the next __syncthreads
       best = lane < GETRF_THREADS / 32 ? wv[lane] : -1.0;
       bi = lane < GETRF_THREADS / 32 ? wi[lane] : 0x7fffffff;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
+      getrf_warp_argmax(best, bi);
       best = __shfl_sync(0xffffffffu, best, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
       const unsigned seq = p.seq_base + (unsigned)j + 1u;
       unsigned long long* hdr = p.ll + (size_t)buf * ((size_t)G * 4 + (size_t)G * GETRF_NB * 2 + (size_t)GETRF_NB * 2);
@@ -139,12 +179,7 @@ __global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfP
             }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
-        if (ov > v || (ov == v && orr < r)) { v = ov; r = orr; }
-      }
+      getrf_warp_argmax(v, r);
       const bool mine = r >= r0 && r < r0 + nr && r != j;     // this CTA stores the old row j at the pivot's position
       {
         const unsigned long long* wrow = rows + (size_t)(r / rp) * GETRF_NB * 2;
@@ -187,24 +222,143 @@ __global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_kernel(const GetrfP
       const T inv = T(1) / piv;
       for (int i = tid; i < nr; i += GETRF_THREADS) {
         if (r0 + i <= j) continue;
-        T l = S[j * rp + i];
-        l = mul ? l * inv : l / piv;
-        S[j * rp + i] = l;
-        if (j + 1 < p.n) {
-          const T x = S[(j + 1) * rp + i] - l * prow[j + 1];
-          S[(j + 1) * rp + i] = x;
-          double v = fabs((double)x);
-          if (v != v) v = __longlong_as_double(0x7ff0000000000000ll);
-          if (v > nbest) { nbest = v; nbi = r0 + i; }
-        }
-#pragma unroll 8
-        for (int k = j + 2; k < p.n; k++) S[k * rp + i] -= l * prow[k];
+        const double a = getrf_update_row<T>(S + i, rp, j, p.n, mul, inv, piv, prow);
+        if (a > nbest) { nbest = a; nbi = r0 + i; }
       }
     }
     // no barrier here: the next column's __syncthreads orders these writes before the first warp reads S, and prow / orow / wv / wi are
     // rewritten only behind it
   }
   __syncthreads();
+  for (int k = 0; k < p.n; k++)
+    for (int i = tid; i < nr; i += GETRF_THREADS) p.A[(long long)k * p.lda + r0 + i] = S[k * rp + i];
+}
+
+// ---- panel kernel, one thread-block cluster -------------------------------------------------------------------------------------
+// Same algorithm and pivot rule as getrf_panel_kernel, for panels whose rows fit the shared memory of ONE cluster (8 CTAs, 16 with the
+// non-portable size): the exchange goes through distributed shared memory instead of L2.  Per column every CTA PUSHES its candidate
+// (magnitude, row, the row's entries) into a slot of every CTA of the cluster, the owner of row j pushes row j, one hardware cluster
+// barrier (barrier.cluster arrive.release / wait.acquire) makes the pushes visible, and from there on every CTA works on local copies:
+// it reduces the candidates itself and has row j of U for its rank-1 update.  Slots alternate with the column parity (a CTA can only
+// push column j + 2 after the barrier of column j + 1, which every CTA reaches after it is done with column j's slots).
+// Two __syncthreads and one cluster barrier per column instead of two L2 round trips.
+constexpr int GETRF_CL_MAX = 16;
+
+template <typename T>
+struct GetrfClusterParams {
+  T* A; long long lda;
+  int m, n;
+  int rows_per_cta;
+  long long* ipiv;
+  int* info;
+  int col_off;
+  double sfmin;
+  long long* dbg;          // probes only: per-phase clock totals of CTA 0 (null = off)
+};
+
+__device__ __forceinline__ void st_cluster_b64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_b32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+template <typename T> __device__ __forceinline__ void st_cluster_val(uint32_t addr, T v);
+template <> __device__ __forceinline__ void st_cluster_val<double>(uint32_t addr, double v) { st_cluster_b64(addr, (unsigned long long)__double_as_longlong(v)); }
+template <> __device__ __forceinline__ void st_cluster_val<float>(uint32_t addr, float v) { st_cluster_b32(addr, __float_as_uint(v)); }
+
+template <typename T>
+__global__ void __launch_bounds__(GETRF_THREADS) getrf_panel_cluster_kernel(const GetrfClusterParams<T> p) {
+  extern __shared__ __align__(16) unsigned char getrf_smem[];
+  T* S = reinterpret_cast<T*>(getrf_smem);                 // S[k * rp + i]: column k, local row i
+  __shared__ T rows_s[2][GETRF_CL_MAX][GETRF_NB];          // candidate rows of every CTA of the cluster
+  __shared__ T rowj_s[2][GETRF_NB];                        // row j before the interchange
+  __shared__ double cval_s[2][GETRF_CL_MAX];
+  __shared__ int cidx_s[2][GETRF_CL_MAX];
+  __shared__ double wv[GETRF_THREADS / 32];
+  __shared__ int wi[GETRF_THREADS / 32];
+  const int CL = gridDim.x, c = (int)cluster_ctarank(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rp = p.rows_per_cta;
+  const int r0 = c * rp, nr = max(0, min(p.m, r0 + rp) - r0);
+  for (int k = 0; k < p.n; k++)
+    for (int i = tid; i < nr; i += GETRF_THREADS) S[k * rp + i] = p.A[(long long)k * p.lda + r0 + i];
+  cluster_sync_all();                                      // every CTA of the cluster is running before the first remote store
+  const int steps = min(p.m, p.n);
+  bool have = false; double nbest = -1.0; int nbi = 0x7fffffff;
+  long long ph[6] = {0, 0, 0, 0, 0, 0}, tprev = clock64();
+#define GETRF_PH(x) do { if (p.dbg) { const long long tn = clock64(); ph[x] += tn - tprev; tprev = tn; } } while (0)
+  for (int j = 0; j < steps; j++) {
+    const int par = j & 1;
+    double best = nbest; int bi = nbi;
+    if (!have) {
+      best = -1.0; bi = 0x7fffffff;
+      for (int i = tid; i < nr; i += GETRF_THREADS) {
+        if (r0 + i < j) continue;
+        double v = fabs((double)S[j * rp + i]);
+        if (v != v) v = __longlong_as_double(0x7ff0000000000000ll);
+        if (v > best) { best = v; bi = r0 + i; }
+      }
+    }
+    getrf_warp_argmax(best, bi);
+    if (lane == 0) { wv[warp] = best; wi[warp] = bi; }
+    GETRF_PH(0);
+    __syncthreads();                                       // also: the previous column's update of S is complete
+    GETRF_PH(1);
+    // every warp finishes the CTA's candidate on its own (8 partial results, one per lane, three exchange rounds)
+    best = wv[lane & (GETRF_THREADS / 32 - 1)]; bi = wi[lane & (GETRF_THREADS / 32 - 1)];
+    getrf_warp_argmax(best, bi);
+    // push: header to slot c of every CTA, candidate row and (owner only) row j; thread (k, r) serves entry k for the CTAs r, r + 4, ...
+    if (tid < CL) {
+      st_cluster_b64(mapa_u32(smem_u32(&cval_s[par][c]), (uint32_t)tid), (unsigned long long)__double_as_longlong(best));
+      st_cluster_b32(mapa_u32(smem_u32(&cidx_s[par][c]), (uint32_t)tid), (uint32_t)bi);
+    }
+    {
+      const int k = tid & (GETRF_NB - 1);
+      const bool own_j = j >= r0 && j < r0 + nr;
+      if (k < p.n && (bi != 0x7fffffff || own_j)) {
+        const T cand = bi != 0x7fffffff ? S[k * rp + (bi - r0)] : T(0);
+        const T rj = own_j ? S[k * rp + (j - r0)] : T(0);
+        const uint32_t a_rows = smem_u32(&rows_s[par][c][k]), a_rowj = smem_u32(&rowj_s[par][k]);
+        for (int r = tid / GETRF_NB; r < CL; r += GETRF_THREADS / GETRF_NB) {
+          if (bi != 0x7fffffff) st_cluster_val<T>(mapa_u32(a_rows, (uint32_t)r), cand);
+          if (own_j) st_cluster_val<T>(mapa_u32(a_rowj, (uint32_t)r), rj);
+        }
+      }
+    }
+    GETRF_PH(2);
+    cluster_sync_all();
+    GETRF_PH(3);
+    // every warp reduces the CL candidates from the local slots (one per lane, four exchange rounds)
+    double v = -1.0; int pr = 0x7fffffff;
+    if ((lane & (GETRF_CL_MAX - 1)) < CL) { v = cval_s[par][lane & (GETRF_CL_MAX - 1)]; pr = cidx_s[par][lane & (GETRF_CL_MAX - 1)]; }
+    getrf_warp_argmax(v, pr);
+    const T* prow = rows_s[par][pr / rp];
+    const T piv = prow[j];
+    if (c == 0 && tid == 0) {
+      p.ipiv[j] = (long long)pr + 1;
+      if (piv == T(0) && *p.info == 0) *p.info = p.col_off + j + 1;
+    }
+    if (pr != j && tid < p.n) {
+      if (j >= r0 && j < r0 + nr) S[tid * rp + (j - r0)] = prow[tid];
+      if (pr >= r0 && pr < r0 + nr) S[tid * rp + (pr - r0)] = rowj_s[par][tid];
+    }
+    __syncthreads();
+    GETRF_PH(4);
+    have = (piv != T(0)) && (j + 1 < p.n);
+    nbest = -1.0; nbi = 0x7fffffff;
+    if (piv != T(0)) {
+      const bool mul = fabs((double)piv) >= p.sfmin;
+      const T inv = T(1) / piv;
+      for (int i = tid; i < nr; i += GETRF_THREADS) {
+        if (r0 + i <= j) continue;
+        const double a = getrf_update_row<T>(S + i, rp, j, p.n, mul, inv, piv, prow);
+        if (a > nbest) { nbest = a; nbi = r0 + i; }
+      }
+    }
+    GETRF_PH(5);
+  }
+#undef GETRF_PH
+  if (p.dbg && c == 0 && tid == 0) for (int x = 0; x < 6; x++) p.dbg[x] = ph[x];
+  cluster_sync_all();                                      // nobody exits while a neighbour may still push into its slots
   for (int k = 0; k < p.n; k++)
     for (int i = tid; i < nr; i += GETRF_THREADS) p.A[(long long)k * p.lda + r0 + i] = S[k * rp + i];
 }

@@ -105,6 +105,7 @@ struct nla_context {
   void* cplx_ws; size_t cplx_ws_bytes;     // planar copies of A and B of a complex call (complex.cuh)
   void* getrf_ws;       // candidate exchange of the LU panel kernel (getrf.cuh); fixed size, allocated on first use
   uint32_t getrf_seq;   // sequence numbers handed out to panel columns so far
+  int getrf_cl[2];      // cluster size of the panel kernel per element type (-1 = not probed yet, 0 = unavailable)
   void* laswp_ws; size_t laswp_ws_bytes;   // interchange plan of nla_laswp / nla_getrf2 (laswp.cuh)
 };
 
@@ -967,7 +968,11 @@ static int make_plan(nla_context* ctx, const Problem& P, Plan& plan, cudaStream_
   if constexpr (!std::is_same<T, double>::value) {
     // Float32 / Float16: tcgen05 GEMMs + tensor-core leaves when both matrices satisfy the TMA constraints (16-byte aligned
     // base and column pitch); cutoff = 128 = the M tile of one tcgen05.mma.  Otherwise the generic strided kernels.
-    if (!ctx->force_simt && ctx->encode && tc_ok<T>(P.A, P.n, P.n, P.lda) && tc_ok<T>(P.B, brows, bcols, P.ldb)) {
+    // A solve with a single diagonal block (n <= 128 -- the reference's own test sizes) stays on the substitution leaf: the tensor-core
+    // leaf needs the block inverted first, a 128-step elimination that costs ~90 us whatever the size (probes/small_n_latency.py:
+    // n = 16 ... 128 solves 100-116 us on the tensor path, 16-20 us here).  With very many right-hand sides the inverse pays again.
+    const bool tiny_solve = P.solve && P.n <= LEAF_MAX && P.m <= 65536;
+    if (!tiny_solve && !ctx->force_simt && ctx->encode && tc_ok<T>(P.A, P.n, P.n, P.lda) && tc_ok<T>(P.B, brows, bcols, P.ldb)) {
       const int64_t nblocks = (P.n + DP_B - 1) / DP_B;
       int64_t ib = pick_inv_block(ctx, P, allow_inv);   // 128: the prepared 128-blocks are the leaves' operands
       bool batched = !P.solve && ctx->trmm_batched && allow_batched;
@@ -1454,7 +1459,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
   ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->gated_macro = 2048; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
-  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0; ctx->getrf_ws = nullptr; ctx->getrf_seq = 0; ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
+  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0; ctx->getrf_ws = nullptr; ctx->getrf_seq = 0; ctx->getrf_cl[0] = ctx->getrf_cl[1] = -1; ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1723,7 +1728,10 @@ int64_t nla_plan(char side, char uplo, char trans, char func, int64_t n, int64_t
   return (int64_t)ops.size();
 }
 
-int64_t nla_leaf_max(int dtype) { return (dtype >= 0 && dtype <= 2) ? LEAF_MAX : -1; }
+// The reference's leaf kernels take a diagonal block of up to 1024 (their shared-memory arrays, src/trsm.jl:9-11); so do these entry points:
+// up to LEAF_MAX in one launch of the leaf kernel, above it through the blocked path (fused slab / block inverses) of the library.
+static const int64_t LEAF_ENTRY_MAX = 1024;
+int64_t nla_leaf_max(int dtype) { return (dtype >= 0 && dtype <= 2) ? LEAF_ENTRY_MAX : -1; }
 
 int nla_rectrxm(nla_handle_t h, char side, char uplo, char trans, char func, int dtype, int64_t n, int64_t m, double alpha,
                 const void* A, int64_t lda, void* B, int64_t ldb, void* stream) {
@@ -1797,9 +1805,10 @@ static int leaf_entry(nla_handle_t h, bool solve, char side, char uplo, int dtyp
   Problem P;
   int rc = make_problem(P, side, uplo, 'N', solve ? 'S' : 'M', dtype, n, m, 1.0, A, lda, B, ldb);
   if (rc != NLA_OK) return rc;
-  if (n > LEAF_MAX) return NLA_ERR_INVALID_DIM;
+  if (n > LEAF_ENTRY_MAX) return NLA_ERR_INVALID_DIM;
   if (n == 0 || m == 0) return NLA_OK;
   NLA_ON_DEVICE(h);
+  if (n > LEAF_MAX) return dispatch(h, P, (cudaStream_t)stream);
   Op o{};
   o.kind = Op::LEAF; o.off = 0; o.sz = n; o.pre = 1.0; o.post = 1.0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -2043,12 +2052,76 @@ static int getrf_panel(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda
   return NLA_OK;
 }
 
+// Cluster size the panel kernel can use on this device: 16 (non-portable) when one such cluster with the largest shared-memory
+// footprint can be resident, else 8, else 0 (grid-wide kernel only).  Probed once per handle and element type.
+template <typename T>
+static int getrf_cluster_size(nla_context* ctx) {
+  int& cached = std::is_same<T, double>::value ? ctx->getrf_cl[0] : ctx->getrf_cl[1];
+  if (cached >= 0) return cached;
+  cached = 0;
+  static const int forced = [] { const char* e = getenv("NLA_GETRF_CLUSTER"); return e ? atoi(e) : -1; }();   // probe hook: 0 / 8 / 16
+  if (forced == 0) return 0;
+  const int smem_cap = 200 * 1024;
+  if (cudaFuncSetAttribute(getrf_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap) != cudaSuccess ||
+      cudaFuncSetAttribute(getrf_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (int cl : {16, 8}) {
+    if (forced > 0 && cl != forced) continue;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cl); cfg.blockDim = dim3(GETRF_THREADS); cfg.dynamicSmemBytes = (size_t)smem_cap;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, getrf_panel_cluster_kernel<T>, &cfg) == cudaSuccess && nclusters >= 1) { cached = cl; break; }
+    cudaGetLastError();
+  }
+  return cached;
+}
+
+// widest panel (power of two, <= GETRF_NB) whose rows fit the shared memory of one cluster; 0 = none
+template <typename T>
+static int64_t getrf_cluster_nb(nla_context* ctx, int64_t m) {
+  const int cl = getrf_cluster_size<T>(ctx);
+  if (cl == 0) return 0;
+  const int64_t rows = (m + cl - 1) / cl;
+  int64_t nb = GETRF_NB;
+  while (nb >= 8 && (size_t)rows * nb * sizeof(T) > (size_t)200 * 1024) nb /= 2;
+  return nb >= 8 ? nb : 0;
+}
+
+template <typename T>
+static int getrf_panel_cluster(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda, long long* ipiv, int* info, int64_t col_off, cudaStream_t st) {
+  const int cl = getrf_cluster_size<T>(ctx);
+  GetrfClusterParams<T> p;
+  p.A = A; p.lda = lda; p.m = (int)m; p.n = (int)n; p.rows_per_cta = (int)((m + cl - 1) / cl); p.ipiv = ipiv; p.info = info; p.col_off = (int)col_off;
+  p.sfmin = std::is_same<T, double>::value ? 2.2250738585072014e-308 : 1.17549435e-38;   // lamch('S')
+  p.dbg = (long long*)ctx->tc_dbg;   // probes only (option "tc_dbg")
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)cl); cfg.blockDim = dim3(GETRF_THREADS); cfg.stream = st;
+  cfg.dynamicSmemBytes = std::max<size_t>(16, (size_t)p.rows_per_cta * n * sizeof(T));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  NLA_CUDA(ctx, (cudaLaunchKernelEx(&cfg, getrf_panel_cluster_kernel<T>, p)));
+  ctx->launches++;
+  return NLA_OK;
+}
+
 template <typename T>
 static int getrf2_rec(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda, long long* ipiv, int* info, int64_t col_off, int64_t nb,
                       cudaStream_t st) {
   const int dtype = std::is_same<T, double>::value ? NLA_F64 : NLA_F32;
   if (m == 1) return getrf_panel<T>(ctx, 1, 1, A, lda, ipiv, info, col_off, st);     // :216-222: ipiv[1] = 1, zero check, nothing else
-  if (n <= nb) return getrf_panel<T>(ctx, m, n, A, lda, ipiv, info, col_off, st);
+  // panels: through one cluster's distributed shared memory when the rows fit it (narrower panels for taller matrices), else grid-wide
+  const int64_t cnb = getrf_cluster_nb<T>(ctx, m);
+  if (cnb > 0) {
+    if (n <= cnb) return getrf_panel_cluster<T>(ctx, m, n, A, lda, ipiv, info, col_off, st);
+  } else if (n <= nb) return getrf_panel<T>(ctx, m, n, A, lda, ipiv, info, col_off, st);
   const int64_t mn = std::min(m, n);
   int64_t n1 = mn / 2;
   if (n1 >= 32) n1 &= ~31ll;

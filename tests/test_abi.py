@@ -33,7 +33,7 @@ def test_status_strings_and_invalid_handle(nla):
     assert lib.nla_workspace_bytes(None, b"L", b"S", 1, 1024, 1024) == -8
     assert lib.nla_destroy(None) == 8
     assert lib.nla_rectrxm(None, b"L", b"L", b"N", b"S", 0, 4, 4, 1.0, None, 4, None, 4, None) == 8
-    assert lib.nla_leaf_max(0) == 128 and lib.nla_leaf_max(7) == -1
+    assert lib.nla_leaf_max(0) == 1024 and lib.nla_leaf_max(7) == -1
 
 
 def test_create_without_gpu_fails_loudly(nla):

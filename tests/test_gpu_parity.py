@@ -184,6 +184,36 @@ def test_leaf_entry_points_fp32(nla, gpu):
                 assert rel(nla.to_numpy(dB), blas) < 1e-5, (n, m, side, uplo, func)
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 1e-5), (np.float16, 1e-2)])
+def test_leaf_entry_points_every_dtype_up_to_the_reference_cap(nla, gpu, dtype, tol):
+    """The reference's leaves accept diagonal blocks up to 1024 (src/trsm.jl:9-11); so do the entry points here, in all three element types:
+    n <= 128 is one launch of the leaf kernel, larger blocks go through the blocked path.  Against the oracle's leaf and OpenBLAS;
+    n = 1025 is rejected."""
+    import torch
+
+    fns = {("L", "L"): (nla.LeftLowerTRSM, nla.LeftLowerTRMM), ("L", "U"): (nla.LeftUpperTRSM, nla.LeftUpperTRMM),
+           ("R", "L"): (nla.RightLowerTRSM, nla.RightLowerTRMM), ("R", "U"): (nla.RightUpperTRSM, nla.RightUpperTRMM)}
+    assert nla.load_library().nla_leaf_max(0) == 1024
+    for n, m in [(16, 5), (128, 64), (200, 48), (512, 130), (1024, 96)]:
+        for (side, uplo), (fs, fm) in fns.items():
+            A, B0 = rp.make_inputs(n, m, side, uplo, dtype, seed=n + m)
+            for f, func in ((fs, "S"), (fm, "M")):
+                dA, dB = nla.colmajor(A), nla.colmajor(B0)
+                gpu.launch_count(reset=True)
+                f(dA, dB)
+                torch.cuda.synchronize()
+                if n <= 128:
+                    assert gpu.launch_count() == 1
+                got = nla.to_numpy(dB)
+                if dtype == np.float64:
+                    assert rel(got, rp.blas_reference(side, uplo, "N", 1.0, func, A, B0)) < tol, (n, m, side, uplo, func)
+                else:
+                    assert rp.error_metric(side, uplo, "N", 1.0, func, A, B0, got) < tol, (n, m, side, uplo, func)
+    A, B0 = rp.make_inputs(1025, 4, "L", "L", dtype, seed=1)
+    with pytest.raises(nla.NextLAError):
+        nla.LeftLowerTRSM(nla.colmajor(A), nla.colmajor(B0))
+
+
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-14), (np.float32, 2e-5)])
 def test_gemm_add_sub(nla, gpu, dtype, tol):
     """GEMM_ADD!(A,B,C): C += A*B and GEMM_SUB!(A,B,C): A -= B*C (src/matmul.jl:69-81), incl. transposed operands.

@@ -151,9 +151,10 @@ int nla_laswp(nla_handle_t handle, int dtype, int64_t rows, int64_t ncols, void 
 /* getrf2!(A, ipiv, info)                                                                  -- src/lu.jl:185-299
  * Recursive LU with partial pivoting of a device matrix, A = P * L * U, every step on the device: the reference's recursion on the
  * columns (split at min(m, n) / 2, :253-256) with laswp (:274, :298), the unit-lower recursive TRSM (:277) and the GEMM update (:280) of
- * this library, and a cooperative panel kernel (getrf.cuh) for blocks of <= 32 columns that applies the reference's single-column rule
- * (:224-251): pivot = first entry of largest magnitude, interchange, scale by the reciprocal (divide when |pivot| < sfmin), a zero pivot
- * leaves the column alone and is reported.
+ * this library, and a panel kernel (getrf.cuh) for blocks of <= 64 columns -- one thread-block cluster exchanging pivot candidates through
+ * distributed shared memory when the panel's rows fit it, a cooperative grid-wide launch otherwise -- that applies the reference's
+ * single-column rule (:224-251): pivot = first entry of largest magnitude, interchange, scale by the reciprocal (divide when
+ * |pivot| < sfmin), a zero pivot leaves the column alone and is reported.
  *   A     m x n, column-major, leading dimension lda >= max(1, m); overwritten by L (unit diagonal not stored) and U
  *   ipiv  DEVICE vector of min(m, n) int64, 1-based: row i was interchanged with row ipiv[i] (the reference's Vector{Int})
  *   info  DEVICE int: 0, or i if U[i, i] is exactly zero (first such i); the reference returns it, a device-side caller reads it after

@@ -253,11 +253,12 @@ static int launch_leaf(nla_context* ctx, const Problem& P, const Op& o, int64_t 
   lp.pre = o.pre; lp.post = o.post;
   const size_t smem = leaf_smem_bytes<T>((int)o.sz);
   const unsigned grid = (unsigned)((nv + LEAF_W - 1) / LEAF_W);
+  const int smem_max = (int)leaf_smem_bytes<T>(LEAF_MAX);   // raised once per handle, not per launch
   if (P.solve) {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(leaf_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int arc = ensure_smem_attr(ctx, leaf_kernel<T, true>, smem_max); if (arc != NLA_OK) return arc; }
     leaf_kernel<T, true><<<grid, LEAF_W, smem, st>>>(lp);
   } else {
-    NLA_CUDA(ctx, cudaFuncSetAttribute(leaf_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int arc = ensure_smem_attr(ctx, leaf_kernel<T, false>, smem_max); if (arc != NLA_OK) return arc; }
     leaf_kernel<T, false><<<grid, LEAF_W, smem, st>>>(lp);
   }
   ctx->launches++;

@@ -11,6 +11,8 @@ Each function cites the reference file:line it follows (paths relative to /root/
   gemm_add/gemm_sub <- src/matmul.jl:69-81 (wrappers), matmul_kernel <- src/matmul.jl:5-66
   *_trsm leaves     <- src/trsm.jl:5-150
   *_trmm leaves     <- src/trmm.jl:43-389
+  laswp             <- src/lu.jl:470-530
+  getrf2            <- src/lu.jl:185-299 (the recursive LU whose TRSM / GEMM steps sit on this path)
 
 Arithmetic is carried out in the element type T of the arrays (float64 / float32 / float16), exactly as
 the Julia kernels do (`eltype(output)` accumulators, src/matmul.jl:18-19,50-54; the final GEMM update is
@@ -335,3 +337,64 @@ def error_metric(side, uplo, trans, alpha, func, A, B0, X) -> float:
         return float(np.linalg.norm(R) / (nA * np.linalg.norm(X64) + abs(alpha) * np.linalg.norm(B64)))
     P = alpha * (Tm @ B64 if side == "L" else B64 @ Tm)
     return float(np.linalg.norm(X64 - P) / (abs(alpha) * nA * np.linalg.norm(B64) + 1e-300))
+
+
+# --------------------------------------------------------------------------------------------
+# Recursive LU  (src/lu.jl) -- SURVEY.md 8(f2)
+# --------------------------------------------------------------------------------------------
+def laswp(A: np.ndarray, first: int, last: int, ipiv: np.ndarray, incx: int) -> None:
+    """src/lu.jl:470-530: rows i and ipiv[i] (1-based) of A are exchanged for i = first..last (incx > 0) or last..first (incx < 0).
+    The reference walks the columns in blocks of 32 (:487-504) and then the remainder (:505-519); the result does not depend on it."""
+    if incx == 0:
+        return
+    rows = range(first, last + 1) if incx > 0 else range(last, first - 1, -1)
+    for i in rows:
+        ip = int(ipiv[i - 1])
+        if ip != i:
+            A[[i - 1, ip - 1], :] = A[[ip - 1, i - 1], :]
+
+
+def getrf2(A: np.ndarray, ipiv: np.ndarray) -> int:
+    """src/lu.jl:185-299, in place on A (m x n, element type kept) and ipiv (1-based, view-relative like the reference's views);
+    returns info (0, or the 1-based index of the first exactly-zero pivot).
+
+    The reference carries `info` as a by-value Int argument and writes `info[] = 1` in the base cases (:219, :247), which cannot update the
+    caller's value; the intent is LAPACK's dgetrf2 (the code is a transcription of it: iinfo propagated as `iinfo + n1`, :260-262, :289-291)
+    and that is what is restated here.  The TRSM / GEMM steps (:277, :280) are BLAS calls in the reference; here they are NumPy in the
+    element type of A."""
+    m, n = A.shape
+    T = A.dtype.type
+    if m == 0 or n == 0:                       # :206
+        return 0
+    if m == 1:                                 # :216-222
+        ipiv[0] = 1
+        return 1 if A[0, 0] == 0 else 0
+    if n == 1:                                 # :224-251
+        sfmin = np.finfo(A.dtype).tiny         # lamch('S')
+        col = A[:, 0]
+        idamax = int(np.argmax(np.abs(col)))   # first index of the largest |.| (np.argmax returns the first maximum)
+        ipiv[0] = idamax + 1
+        if col[idamax] == 0:
+            return 1
+        if idamax != 0:
+            col[0], col[idamax] = col[idamax], col[0]
+        if abs(col[0]) >= sfmin:
+            col[1:] *= T(1) / col[0]           # BLAS.scal! by the reciprocal (:240)
+        else:
+            col[1:] /= col[0]                  # :242
+        return 0
+    n1 = min(m, n) // 2                        # :254
+    info = getrf2(A[:, :n1], ipiv[:n1])        # :258
+    laswp(A[:, n1:], 1, n1, ipiv, 1)           # :274
+    L11 = np.tril(A[:n1, :n1], -1).astype(A.dtype) + np.eye(n1, dtype=A.dtype)
+    A12 = A[:n1, n1:]
+    for i in range(1, n1):                     # trsm!('L','L','N','U') (:277): forward substitution with a unit diagonal
+        A12[i, :] -= (L11[i, :i] @ A12[:i, :]).astype(A.dtype)
+    A[n1:, n1:] -= (A[n1:, :n1] @ A12).astype(A.dtype)      # gemm!('N','N',-1,...,1) (:280)
+    k = min(m, n)
+    iinfo = getrf2(A[n1:, n1:], ipiv[n1:k])    # :284
+    if info == 0 and iinfo > 0:                # :289-291
+        info = iinfo + n1
+    ipiv[n1:k] += n1                           # :293-295
+    laswp(A[:, :n1], n1 + 1, k, ipiv, 1)       # :298
+    return info

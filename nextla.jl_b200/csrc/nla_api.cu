@@ -1495,7 +1495,7 @@ int nla_destroy(nla_handle_t h) {
   if (h->stream_dev) { if (h->stream_dev_async) cudaFreeAsync(h->stream_dev, 0); else cudaFree(h->stream_dev); }
   if (h->stream_flags_host) cudaFreeHost(h->stream_flags_host);
   if (h->cplx_ws) cudaFreeAsync(h->cplx_ws, 0);
-  if (h->getrf_ws) cudaFree(h->getrf_ws);
+  if (h->getrf_ws) cudaFreeAsync(h->getrf_ws, 0);
   if (h->laswp_ws) cudaFreeAsync(h->laswp_ws, 0);
   if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
   if (h->prep_event) cudaEventDestroy(h->prep_event);
@@ -2030,7 +2030,7 @@ static int getrf_panel(nla_context* ctx, int64_t m, int64_t n, T* A, int64_t lda
   const int G = (int)((m + rows - 1) / rows);
   if (!ctx->getrf_ws) {
     const size_t bytes = getrf_ll_words(G_max) * sizeof(unsigned long long);
-    NLA_CUDA(ctx, cudaMalloc(&ctx->getrf_ws, bytes));
+    NLA_CUDA(ctx, cudaMallocAsync(&ctx->getrf_ws, bytes, st));   // stream-ordered: the call stays asynchronous on first use too
     NLA_CUDA(ctx, cudaMemsetAsync(ctx->getrf_ws, 0, bytes, st));
     ctx->ws_allocs++;
     ctx->getrf_seq = 0;

@@ -233,6 +233,8 @@ int nla_gemm_update(nla_handle_t handle, int dtype, char transa, char transb, in
  *                 the call stays asynchronous.  0 = off: the solve is then only conditionally stable (error ~ eps * cond(block)).
  *   "inv_guard_kappa" threshold override of the guard (0 = the default above; 1 rejects every block = substitution leaves everywhere)
  *   "nvtx"        1 = NVTX ranges around every call and schedule op (nsys / ncu --nvtx)
+ *   "getrf_cluster" nla_getrf2 panels: -1 (default) = one thread-block cluster of 16 CTAs (8 if the device refuses 16) whenever the
+ *                 panel's rows fit its shared memory, else the grid-wide cooperative kernel; 0 = grid-wide kernel only; 8 / 16 = that size
  *   "profile"     1 = bracket every kernel launch with CUDA events (read back with nla_profile_read)
  * Read-only keys of nla_get_option:
  *     "inv_fallbacks" (synchronises) number of blocks of the last guarded solve that took the substitution fallback

@@ -106,6 +106,7 @@ struct nla_context {
   void* getrf_ws;       // candidate exchange of the LU panel kernel (getrf.cuh); fixed size, allocated on first use
   uint32_t getrf_seq;   // sequence numbers handed out to panel columns so far
   int getrf_cl[2];      // cluster size of the panel kernel per element type (-1 = not probed yet, 0 = unavailable)
+  int64_t getrf_cluster;   // option: -1 automatic, 0 = grid-wide panel kernel only, 8 / 16 = that cluster size
   void* laswp_ws; size_t laswp_ws_bytes;   // interchange plan of nla_laswp / nla_getrf2 (laswp.cuh)
 };
 
@@ -1460,7 +1461,7 @@ int nla_create(nla_handle_t* handle, int device) {
   for (auto& e : ctx->host_events) e = nullptr;
   ctx->user_ws = nullptr; ctx->user_ws_bytes = 0; ctx->ws_allocs = 0; ctx->inv_guard = 1; ctx->cond_ws = nullptr; ctx->cond_ws_bytes = 0;
   ctx->slab_w = 0; ctx->slab_kind = 0; ctx->host_macro = 1024; ctx->host_macro_mid = 1024; ctx->host_stream = 1; ctx->gated_stream = 0; ctx->gated_macro = 2048; ctx->stream_dev = nullptr; ctx->stream_dev_ints = 0; ctx->stream_dev_async = 0;
-  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0; ctx->getrf_ws = nullptr; ctx->getrf_seq = 0; ctx->getrf_cl[0] = ctx->getrf_cl[1] = -1; ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
+  ctx->stream_flags_host = ctx->stream_flags_dev = nullptr; ctx->stream_flags_n = 0; ctx->write_value32 = nullptr; ctx->nvtx = 0; ctx->inv_guard_kappa = 0; ctx->cond_blocks = 0; ctx->lauum_ws = nullptr; ctx->lauum_ws_bytes = 0; ctx->cplx_ws = nullptr; ctx->cplx_ws_bytes = 0; ctx->getrf_ws = nullptr; ctx->getrf_seq = 0; ctx->getrf_cl[0] = ctx->getrf_cl[1] = -1; ctx->getrf_cluster = -1; ctx->laswp_ws = nullptr; ctx->laswp_ws_bytes = 0;
   DeviceGuard dg(device);
   if (dg.err != cudaSuccess) { delete ctx; return NLA_ERR_CUDA; }
   cudaDriverEntryPointQueryResult qr;
@@ -1539,6 +1540,10 @@ int nla_set_option(nla_handle_t h, const char* key, int64_t value) {
   if (!strcmp(key, "inv_guard")) { h->inv_guard = value != 0; return NLA_OK; }
   if (!strcmp(key, "inv_guard_kappa")) { if (value < 0) return NLA_ERR_INVALID_DIM; h->inv_guard_kappa = value; return NLA_OK; }
   if (!strcmp(key, "nvtx")) { h->nvtx = value != 0; return NLA_OK; }
+  if (!strcmp(key, "getrf_cluster")) {
+    if (value != -1 && value != 0 && value != 8 && value != 16) return NLA_ERR_INVALID_DIM;
+    h->getrf_cluster = value; h->getrf_cl[0] = h->getrf_cl[1] = -1; return NLA_OK;
+  }
   if (!strcmp(key, "tc_dbg")) { h->tc_dbg = value; return NLA_OK; }
   if (!strcmp(key, "tc_chunk_k")) { if (value < 0 || value >= (1ll << 31)) return NLA_ERR_INVALID_DIM; h->tc_chunk_k = value; return NLA_OK; }
   if (!strcmp(key, "streams")) { if (value < 0 || value > 16) return NLA_ERR_INVALID_DIM; h->nstreams = value; return NLA_OK; }
@@ -1574,6 +1579,7 @@ int64_t nla_get_option(nla_handle_t h, const char* key) {
   if (!strcmp(key, "host_slabs")) return h->host_slabs;
   if (!strcmp(key, "inv_guard")) return h->inv_guard;
   if (!strcmp(key, "inv_guard_kappa")) return h->inv_guard_kappa;
+  if (!strcmp(key, "getrf_cluster")) return h->getrf_cluster;
   if (!strcmp(key, "inv_fallbacks")) {   // read-only, synchronises: blocks of the LAST guarded solve that took the substitution fallback
     if (!h->cond_ws || h->cond_blocks <= 0) return 0;
     DeviceGuard dg(h->device);
@@ -2060,7 +2066,7 @@ static int getrf_cluster_size(nla_context* ctx) {
   int& cached = std::is_same<T, double>::value ? ctx->getrf_cl[0] : ctx->getrf_cl[1];
   if (cached >= 0) return cached;
   cached = 0;
-  static const int forced = [] { const char* e = getenv("NLA_GETRF_CLUSTER"); return e ? atoi(e) : -1; }();   // probe hook: 0 / 8 / 16
+  const int forced = (int)ctx->getrf_cluster;   // option "getrf_cluster": -1 automatic, 0 grid-wide kernel only, 8 / 16 that cluster size
   if (forced == 0) return 0;
   const int smem_cap = 200 * 1024;
   if (cudaFuncSetAttribute(getrf_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap) != cudaSuccess ||

@@ -187,7 +187,7 @@ def test_getrf2_against_the_oracle_and_the_frozen_vectors(nla, gpu):
 
 @pytest.mark.parametrize("m,n", [(300, 257), (640, 640), (500, 900)])
 def test_getrf2_matches_the_oracle_live(nla, gpu, m, n):
-    """The oracle run live on seeded inputs beyond the frozen sizes (several panels, the cluster and the grid-wide panel kernel)."""
+    """The oracle run live on seeded inputs beyond the frozen sizes (several panels per factorisation)."""
     sys_path_oracle()
     from oracle import reference_port as rp
 
@@ -209,3 +209,44 @@ def sys_path_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
         sys.path.insert(0, root)
+
+
+@pytest.mark.parametrize("cluster", [0, 8, 16])
+def test_getrf2_every_panel_kernel(nla, gpu, cluster):
+    """Option getrf_cluster: 0 = the grid-wide cooperative panel kernel (what very tall panels get), 8 / 16 = one cluster of that size.
+    Same pivots and factors as LAPACK whichever kernel factors the panels; Float32 by residual."""
+    from scipy.linalg import lu_factor
+
+    gpu.set_option("getrf_cluster", cluster)
+    try:
+        for m, n in [(1, 1), (70, 33), (257, 300), (1500, 900), (2100, 2100)]:
+            rng = np.random.RandomState(m * 7 + n + cluster)
+            A0 = rng.rand(m, n) - 0.5
+            LU, piv, info = factor(nla, A0)
+            lu_ref, piv_ref = lu_factor(A0, check_finite=False)
+            assert info == 0 and np.array_equal(piv, piv_ref[:min(m, n)]), (cluster, m, n)
+            assert np.linalg.norm(LU - lu_ref) / np.linalg.norm(lu_ref) < 1e-10
+        A32 = (np.random.RandomState(cluster).rand(1200, 1000) - 0.5).astype(np.float32)
+        LU, piv, info = factor(nla, A32)
+        assert info == 0
+        check_lu(A32, LU, piv, 5e-5)
+        Z = np.random.RandomState(5).rand(300, 300) - 0.5
+        Z[:, 123] = 0.0
+        _, _, info = factor(nla, Z)
+        assert info == 124
+    finally:
+        gpu.set_option("getrf_cluster", -1)
+
+
+def test_getrf2_panel_taller_than_a_cluster(nla, gpu):
+    """60000 rows: more than 16 CTAs' shared memory holds even for 8-column panels in Float64, so the panels go to the grid-wide kernel
+    with a narrower width (32 columns: 406 rows per CTA)."""
+    from scipy.linalg import lu_factor
+
+    m, n = 60000, 96
+    rng = np.random.RandomState(60)
+    A0 = rng.rand(m, n) - 0.5
+    LU, piv, info = factor(nla, A0)
+    lu_ref, piv_ref = lu_factor(A0, check_finite=False)
+    assert info == 0 and np.array_equal(piv, piv_ref)
+    assert np.linalg.norm(LU - lu_ref) / np.linalg.norm(lu_ref) < 1e-10

@@ -704,7 +704,7 @@ def test_options_round_trip(nla, gpu):
     assert {"leaf", "macro", "streams", "tc_bn", "tc_cg", "inv_block", "tc_persist", "right_via_left", "trmm_batched", "pdl", "profile"} <= set(keys)
     for k in keys:
         old = gpu.get_option(k)
-        assert old >= 0 or (k == "macro" and old == -1), k   # "macro": -1 = automatic
+        assert old >= 0 or (k in ("macro", "getrf_cluster") and old == -1), k   # -1 = automatic
         gpu.set_option(k, old)
         assert gpu.get_option(k) == old, k
     with pytest.raises(nla.NextLAError):

@@ -250,3 +250,36 @@ def test_getrf2_panel_taller_than_a_cluster(nla, gpu):
     lu_ref, piv_ref = lu_factor(A0, check_finite=False)
     assert info == 0 and np.array_equal(piv, piv_ref)
     assert np.linalg.norm(LU - lu_ref) / np.linalg.norm(lu_ref) < 1e-10
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.float16])
+def test_laswp_arbitrary_pivots(nla, gpu, dtype):
+    """nla_laswp (src/lu.jl:470-530) with pivot vectors a factorisation would never produce: partners above the row, repeated partners,
+    self-interchanges, ranges that are not multiples of the kernel's batch of 16, forward and backward walks, a column view with
+    lda > rows.  The planned kernel (laswp.cuh) must reproduce the sequential walk of the oracle bit for bit."""
+    import torch
+
+    sys_path_oracle()
+    from oracle import reference_port as rp
+
+    rng = np.random.RandomState(11)
+    for rows, cols, k1, k2 in [(300, 70, 1, 300), (300, 70, 17, 211), (64, 5, 1, 64), (1000, 333, 3, 999), (40, 1, 1, 40), (513, 129, 100, 131)]:
+        for incx in (1, -1):
+            for kind in ("random", "few_targets", "self", "above"):
+                if kind == "random":
+                    piv = rng.randint(1, rows + 1, size=rows)
+                elif kind == "few_targets":
+                    piv = rng.choice([1, rows, rows // 2 + 1], size=rows)
+                elif kind == "self":
+                    piv = np.arange(1, rows + 1)
+                    piv[::3] = rng.randint(1, rows + 1, size=len(piv[::3]))
+                else:
+                    piv = np.maximum(1, np.arange(1, rows + 1) - rng.randint(0, 20, size=rows))
+                piv = piv.astype(np.int64)
+                big = (rng.rand(rows + 8, cols + 3) - 0.5).astype(dtype)
+                want = big.copy()
+                rp.laswp(want[:rows, 1:cols + 1], k1, k2, piv, incx)
+                dbig = nla.colmajor(big)
+                nla.laswp(dbig[:rows, 1:cols + 1], k1, k2, torch.from_numpy(piv).cuda(), incx)
+                torch.cuda.synchronize()
+                assert np.array_equal(nla.to_numpy(dbig), want), (rows, cols, k1, k2, incx, kind)

@@ -266,6 +266,48 @@ def timed_steps(torch, dist, world, step, restore, steps, warmup, dev, min_warm_
     return total.item()
 
 
+def run_lu_leg(torch, nla, dev, n, steps, warmup):
+    """SURVEY.md 8(f2), not part of BASELINE.json's metric: the reference's recursive LU (getrf2!, src/lu.jl:185-299) through nla_getrf2 on
+    a random Float64 matrix resident in HBM; 2/3 n^3 flops; residual ||P A - L U||_F / ||A||_F checked once with an FP64 product."""
+    import numpy as np
+
+    g = torch.Generator(device=dev).manual_seed(77)
+    A0 = (torch.rand(n, n, dtype=torch.float64, device=dev, generator=g) - 0.5).t()
+    A = torch.empty_like(A0, memory_format=torch.preserve_format)
+    ipiv = torch.empty(n, dtype=torch.int64, device=dev)
+    info = torch.zeros((), dtype=torch.int32, device=dev)
+    times = []
+    for it in range(warmup + steps):
+        A.copy_(A0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nla.getrf2(A, ipiv, info)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    perm = np.arange(n)
+    for i, p in enumerate((ipiv - 1).cpu().numpy()):
+        if p != i:
+            perm[i], perm[p] = perm[p], perm[i]
+    R = A0[torch.from_numpy(perm).to(dev)]
+    L = torch.tril(A, -1)
+    L.diagonal().fill_(1.0)
+    R -= L @ torch.triu(A)
+    res = float(torch.linalg.norm(R) / torch.linalg.norm(A0))
+    del R, L
+    flops = 2.0 / 3.0 * float(n) ** 3
+    out = {"config": f"LU: Float64 getrf2! (recursive, partial pivoting) n = {n}, whole factorisation on the device (nla_getrf2)",
+           "note": "SURVEY.md 8(f2) row, outside BASELINE.json's metric", "dtype": "f64", "value": flops / ms / 1e9, "unit": "TFLOP/s",
+           "ms_per_step": ms, "steps": steps, "info": int(info.item()), "residual": res, "tolerance": 1e-12}
+    assert res < 1e-12 and out["info"] == 0, out
+    del A, A0
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_extra_leg(torch, dist, nla, sharded, h, world, rank, dev, name, dts, side, uplo, trans, func, n, m_local, steps, warmup, peaks, note):
     """One extra leg: synthetic inputs on the device, A owned by rank 0 and broadcast (pipelined) inside every step when world > 1."""
     dt = getattr(torch, dts)
@@ -640,6 +682,13 @@ def main():
                 extra.append(run_extra_leg(torch, dist, nla, sharded, h, world, rank, dev, name, dts, sd, up, tr, fn, nn, mm, xs, xw, peaks, note))
             except Exception as e:  # noqa: BLE001
                 extra.append({"config": name, "error": repr(e)})
+                torch.cuda.empty_cache()
+
+        if world == 1:
+            try:
+                extra.append(run_lu_leg(torch, nla, dev, 16384, xs, xw))
+            except Exception as e:  # noqa: BLE001
+                extra.append({"config": "LU: Float64 getrf2! n = 16384", "error": repr(e)})
                 torch.cuda.empty_cache()
 
     if rank == 0:

@@ -229,7 +229,7 @@ def test_getrf2_every_panel_kernel(nla, gpu, cluster):
         A32 = (np.random.RandomState(cluster).rand(1200, 1000) - 0.5).astype(np.float32)
         LU, piv, info = factor(nla, A32)
         assert info == 0
-        check_lu(A32, LU, piv, 5e-5)
+        check_lu(A32, LU, piv, 1e-4)
         Z = np.random.RandomState(5).rand(300, 300) - 0.5
         Z[:, 123] = 0.0
         _, _, info = factor(nla, Z)

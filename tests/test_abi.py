@@ -34,6 +34,8 @@ def test_status_strings_and_invalid_handle(nla):
     assert lib.nla_destroy(None) == 8
     assert lib.nla_rectrxm(None, b"L", b"L", b"N", b"S", 0, 4, 4, 1.0, None, 4, None, 4, None) == 8
     assert lib.nla_leaf_max(0) == 1024 and lib.nla_leaf_max(7) == -1
+    assert lib.nla_getrf2(None, 0, 4, 4, None, 4, None, None, None) == 8 and lib.nla_lauum(None, b"L", 0, 4, None, 4, 2, None) == 8
+    assert lib.nla_laswp(None, 0, 4, 4, None, 4, 1, 4, None, 1, None) == 8
 
 
 def test_create_without_gpu_fails_loudly(nla):

@@ -144,7 +144,9 @@ int nla_memcpy2d_async(nla_handle_t handle, void *dst, int64_t dst_pitch_bytes, 
  * Row interchanges on a device matrix (rows x ncols, column-major): for i = k1..k2 (incx = 1) or k2..k1 (incx = -1) swap rows i and
  * ipiv[i] (1-based, like the reference; ipiv is a DEVICE vector of int64 = Julia Int, entries outside [k1, k2] are not read).  With
  * nla_trxm(..., diag = 'U') and nla_gemm_update this runs the laswp + TRSM + GEMM steps of the reference's recursive LU
- * (getrf2!, src/lu.jl:274-280, :297) on the device; the panel factorisation stays with the caller. */
+ * (getrf2!, src/lu.jl:274-280, :297) on the device; nla_getrf2 below is the whole factorisation.
+ * A forward walk is planned once per call (which row ends where, in batches of 16 pivots) and applied with independent gathers and
+ * scatters; a backward walk goes pivot by pivot. */
 int nla_laswp(nla_handle_t handle, int dtype, int64_t rows, int64_t ncols, void *A, int64_t lda, int64_t k1, int64_t k2,
               const int64_t *ipiv, int incx, void *stream);
 

@@ -1,8 +1,8 @@
 // laswp.cuh -- row interchanges on a device matrix: the device-side counterpart of the reference's `laswp`
 // (src/lu.jl:470-530), which its recursive LU applies between the panel factorisation and the TRSM + GEMM update
 // (src/lu.jl:274, :297).  With nla_trxm (unit-lower solve) and nla_gemm_update this puts every O(n^3) step of getrf2! on the
-// device; the panel factorisation itself stays with the caller.
-// One thread per column walks the pivots in order (interchanges of one column are sequentially dependent, columns are
+// device; since round 2 the panel factorisation is on the device too (getrf.cuh, nla_getrf2).
+// laswp_kernel (backward walks): one thread per column walks the pivots in order (interchanges of one column are sequentially dependent, columns are
 // independent); the pivot vector is read through the read-only path and broadcast to the warp.
 #pragma once
 #include "common.cuh"
